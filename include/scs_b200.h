@@ -1,0 +1,267 @@
+/*
+ * scs_b200.h -- C ABI of the B200-native ADMM hot path for SCS (cvxgrp/scs 3.2.11).
+ *
+ * Everything here is `extern "C"`, plain pointers and sizes.  Three groups:
+ *
+ *  (1) the OUTER ABI -- scs_init / scs_update / scs_solve / scs_finish / scs /
+ *      scs_set_default_settings / scs_version and the data structs.  The struct
+ *      layouts are byte-for-byte those of the reference build with
+ *      DLONG=0, SFLOAT=0 and no spectral cones (reference include/scs.h:47-244,
+ *      include/aa_stats.h:21-42, include/scs_types.h:16-30), so a caller
+ *      compiled against the reference headers can link this library instead.
+ *
+ *  (2) the LINEAR-SYSTEM PLUGIN ABI -- the five link-time symbols every SCS
+ *      backend defines (reference include/linsys.h:25-71).  Host pointers in and
+ *      out, exactly as the stock src/scs.c calls them (scs.c:1092,1127,763,1220).
+ *
+ *  (3) OPERATOR-LEVEL entry points (scs_b200_*): the cone projection, Anderson
+ *      acceleration and SpMV operators of the hot path callable one at a time
+ *      with host buffers.  The reference keeps these internal
+ *      (include/cones.h:80-90, include/aa.h:66-143, linsys/scs_matrix.h); they are
+ *      exported here so the parity tests can compare operator by operator.
+ *
+ * All compute happens in hand-written sm_100a CUDA kernels; there is no CPU
+ * fallback: every entry point fails (NULL / nonzero / SCS_FAILED) when no CUDA
+ * device is usable.
+ */
+#ifndef SCS_B200_H
+#define SCS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* primitive types: reference include/scs_types.h (DLONG=0, SFLOAT=0) */
+typedef int scs_int;
+typedef double scs_float;
+
+#define SCS_NULL 0
+
+/* exit flags: reference include/scs.h:33-42 */
+#define SCS_INFEASIBLE_INACCURATE (-7)
+#define SCS_UNBOUNDED_INACCURATE (-6)
+#define SCS_SIGINT (-5)
+#define SCS_FAILED (-4)
+#define SCS_INDETERMINATE (-3)
+#define SCS_INFEASIBLE (-2)
+#define SCS_UNBOUNDED (-1)
+#define SCS_UNFINISHED (0)
+#define SCS_SOLVED (1)
+#define SCS_SOLVED_INACCURATE (2)
+
+/* opaque workspaces */
+typedef struct SCS_WORK ScsWork;
+typedef struct SCS_LIN_SYS_WORK ScsLinSysWork;
+typedef struct SCS_B200_CONE_WORK ScsB200ConeWork;
+typedef struct SCS_B200_AA_WORK ScsB200AaWork;
+
+/* CSC sparse matrix, zero-based (reference include/scs.h:47-58). */
+typedef struct {
+  scs_float *x; /* values, nnz */
+  scs_int *i;   /* row indices, nnz */
+  scs_int *p;   /* column pointers, n+1 */
+  scs_int m;    /* rows */
+  scs_int n;    /* cols */
+} ScsMatrix;
+
+/* solver settings (reference include/scs.h:61-101; defaults glbopts.h:35-50) */
+typedef struct {
+  scs_int normalize;
+  scs_float scale;
+  scs_int adaptive_scale;
+  scs_float rho_x;
+  scs_int max_iters;
+  scs_float eps_abs;
+  scs_float eps_rel;
+  scs_float eps_infeas;
+  scs_float alpha;
+  scs_float time_limit_secs;
+  scs_int verbose;
+  scs_int warm_start;
+  scs_int acceleration_lookback;
+  scs_int acceleration_interval;
+  scs_int acceleration_type_1;
+  scs_float acceleration_regularization;
+  scs_float acceleration_relaxation;
+  const char *write_data_filename;
+  const char *log_csv_filename;
+} ScsSettings;
+
+/* problem data (reference include/scs.h:104-119) */
+typedef struct {
+  scs_int m;
+  scs_int n;
+  ScsMatrix *A; /* m x n */
+  ScsMatrix *P; /* n x n upper triangle, or NULL */
+  scs_float *b; /* m */
+  scs_float *c; /* n */
+} ScsData;
+
+/* cone product K, rows of A in this order (reference include/scs.h:122-172) */
+typedef struct {
+  scs_int z;      /* zero cone rows */
+  scs_int l;      /* nonnegative orthant rows */
+  scs_float *bu;  /* box upper, bsize-1 */
+  scs_float *bl;  /* box lower, bsize-1 */
+  scs_int bsize;  /* box cone total length (incl. t) */
+  scs_int *q;     /* second-order cone sizes */
+  scs_int qsize;
+  scs_int *s;     /* PSD cone matrix orders */
+  scs_int ssize;
+  scs_int *cs;    /* complex PSD orders  (not supported by the device path) */
+  scs_int cssize;
+  scs_int ep;     /* primal exp triples  (not supported by the device path) */
+  scs_int ed;     /* dual exp triples    (not supported by the device path) */
+  scs_float *p;   /* power cone params   (not supported by the device path) */
+  scs_int psize;
+} ScsCone;
+
+/* solution / certificate (reference include/scs.h:180-187) */
+typedef struct {
+  scs_float *x;
+  scs_float *y;
+  scs_float *s;
+} ScsSolution;
+
+/* AA lifetime counters (reference include/aa_stats.h:21-42) */
+typedef struct {
+  scs_int iter;
+  scs_int n_accept;
+  scs_int n_reject_lapack;
+  scs_int n_reject_rank0;
+  scs_int n_reject_nonfinite;
+  scs_int n_reject_weight_cap;
+  scs_int n_safeguard_reject;
+  scs_int last_rank;
+  scs_float last_aa_norm;
+  scs_float last_regularization;
+} AaStats;
+
+/* solve report; times in milliseconds (reference include/scs.h:190-244) */
+typedef struct {
+  scs_int iter;
+  char status[128];
+  char lin_sys_solver[128];
+  scs_int status_val;
+  scs_int scale_updates;
+  scs_float pobj;
+  scs_float dobj;
+  scs_float res_pri;
+  scs_float res_dual;
+  scs_float gap;
+  scs_float res_infeas;
+  scs_float res_unbdd_a;
+  scs_float res_unbdd_p;
+  scs_float setup_time;
+  scs_float solve_time;
+  scs_float scale;
+  scs_float comp_slack;
+  scs_int rejected_accel_steps;
+  scs_int accepted_accel_steps;
+  AaStats aa_stats;
+  scs_float lin_sys_time;
+  scs_float cone_time;
+  scs_float accel_time;
+} ScsInfo;
+
+/* ------------------------------------------------------------------ (1) --
+ * Outer ABI.  Replaces reference include/scs.h:271-338 / src/scs.c:1245-1551.
+ * The ADMM iteration (scs.c:1356-1455) runs with all iterates resident in HBM;
+ * the host sees scalars only (every CONVERGED_INTERVAL=25 iterations) and the
+ * solution at the end. */
+ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs);
+scs_int scs_update(ScsWork *w, scs_float *b, scs_float *c);
+scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info,
+                  scs_int warm_start);
+void scs_finish(ScsWork *w);
+scs_int scs(const ScsData *d, const ScsCone *k, const ScsSettings *stgs,
+            ScsSolution *sol, ScsInfo *info);
+void scs_set_default_settings(ScsSettings *stgs);
+const char *scs_version(void);
+
+/* ------------------------------------------------------------------ (2) --
+ * Linear-system plugin ABI.  Replaces reference linsys/cpu/indirect/private.c
+ * :221-349 and linsys/gpu/indirect/private.c:204-527.  A, P, diag_r are HOST
+ * pointers (borrowed only during the call; copied to the device).  `b` (n+m)
+ * and `s` (n or NULL) are HOST pointers; `b` is overwritten with [x; y]. */
+ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
+                                     const scs_float *diag_r);
+void scs_free_lin_sys_work(ScsLinSysWork *w);
+scs_int scs_solve_lin_sys(ScsLinSysWork *w, scs_float *b, const scs_float *s,
+                          scs_float tol);
+scs_int scs_update_lin_sys_diag_r(ScsLinSysWork *w,
+                                  const scs_float *new_diag_r);
+const char *scs_get_lin_sys_method(void);
+
+/* ------------------------------------------------------------------ (3) --
+ * Operator-level entry points (host buffers; used by tests/ and bench.py). */
+
+/* CG iterations used by the most recent scs_solve_lin_sys, and the running
+ * total (reference private.h:29 tot_cg_its). */
+scs_int scs_b200_linsys_last_cg_its(const ScsLinSysWork *w);
+long long scs_b200_linsys_total_cg_its(const ScsLinSysWork *w);
+
+/* y (+)= A x  and  y (+)= A' x  through the device SpMV kernels
+ * (reference linsys/scs_matrix.c:161-203 accum_by_atrans / accum_by_a).
+ * x, y are HOST arrays; accumulate != 0 adds into the incoming y. */
+scs_int scs_b200_accum_by_a(ScsLinSysWork *w, const scs_float *x, scs_float *y,
+                            scs_int accumulate);
+scs_int scs_b200_accum_by_atrans(ScsLinSysWork *w, const scs_float *x,
+                                 scs_float *y, scs_int accumulate);
+
+/* Time `reps` back-to-back launches of one device SpMV (op 0: A x via the
+ * row-major copy, op 1: A' x via the CSC arrays) with CUDA events; inputs
+ * resident in HBM.  Returns average milliseconds per launch, <0 on error.
+ * *alg_bytes receives the algorithmic bytes of one launch. */
+double scs_b200_time_spmv(ScsLinSysWork *w, scs_int op, scs_int reps,
+                          double *alg_bytes);
+/* Time `reps` CG iterations (4 kernels each) the same way. */
+double scs_b200_time_cg_iter(ScsLinSysWork *w, scs_int reps, double *alg_bytes);
+
+/* Cone operator: replaces reference src/cones.c:1498-1596 (init_cone /
+ * proj_dual_cone / finish_cone) for zero, LP, box, SOC and PSD cones.
+ * D is the row scaling of the equilibrated problem (length m) or NULL
+ * (reference normalize_box_cone, cones.c:1160-1177).  x (length m) and r_y
+ * (length m or NULL) are HOST arrays; x is projected in place onto the dual
+ * cone under the R-metric. Returns 0, or <0 on failure. */
+ScsB200ConeWork *scs_b200_init_cone(const ScsCone *k, scs_int m,
+                                    const scs_float *D);
+scs_int scs_b200_proj_dual_cone(ScsB200ConeWork *c, scs_float *x,
+                                const scs_float *r_y);
+void scs_b200_finish_cone(ScsB200ConeWork *c);
+
+/* Anderson acceleration operator: replaces reference src/aa.c:657-979
+ * (aa_init / aa_apply / aa_safeguard / aa_reset / aa_finish / aa_get_stats).
+ * f, x, f_new, x_new are HOST arrays of length dim. */
+ScsB200AaWork *scs_b200_aa_init(scs_int dim, scs_int mem, scs_int min_len,
+                                scs_int type1, scs_float regularization,
+                                scs_float relaxation,
+                                scs_float safeguard_factor,
+                                scs_float max_weight_norm,
+                                scs_int ir_max_steps, scs_int verbosity);
+scs_float scs_b200_aa_apply(ScsB200AaWork *a, scs_float *f, const scs_float *x);
+scs_int scs_b200_aa_safeguard(ScsB200AaWork *a, scs_float *f_new,
+                              scs_float *x_new);
+void scs_b200_aa_reset(ScsB200AaWork *a);
+void scs_b200_aa_finish(ScsB200AaWork *a);
+AaStats scs_b200_aa_get_stats(const ScsB200AaWork *a);
+
+/* Per-solve device statistics of the last scs_solve on this workspace. */
+typedef struct {
+  long long cg_iters;        /* total CG iterations */
+  long long lin_sys_solves;  /* scs_solve_lin_sys calls */
+  long long kernel_launches; /* kernels of this library launched */
+  double spmv_ms;            /* reserved */
+  scs_int n_gpus;
+} ScsB200Stats;
+scs_int scs_b200_get_stats(const ScsWork *w, ScsB200Stats *out);
+
+/* Number of kernels this library has launched in this process. */
+long long scs_b200_launch_count(void);
+/* 1 if a CUDA device of compute capability 10.x is usable, else 0. */
+scs_int scs_b200_device_ok(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCS_B200_H */

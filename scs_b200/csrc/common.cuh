@@ -1,0 +1,180 @@
+// common.cuh -- device-side helpers shared by all kernels of the B200 SCS hot path.
+//
+// * deterministic block reductions (fixed shuffle tree + fixed smem order)
+// * "last block finishes" grid reductions: every block writes its partial to a
+//   fixed slot, the last block to arrive sums the slots in index order, so a
+//   launch with a fixed grid is bit-reproducible (no fp64 atomics anywhere)
+// * sm_100a TMA 1-D bulk copy + mbarrier wrappers (cp.async.bulk -> SASS UBLKCP)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define B200_NUM_SMS_FALLBACK 148
+#define B200_RED_THREADS 512  // threads per block of every reduction-carrying vector kernel
+#define B200_MAX_PARTIALS 2048
+
+#define CUDA_OK(call)                                                        \
+  do {                                                                       \
+    cudaError_t e__ = (call);                                                \
+    if (e__ != cudaSuccess) {                                                \
+      b200_set_error(#call, e__, __FILE__, __LINE__);                        \
+      return -1;                                                             \
+    }                                                                        \
+  } while (0)
+
+extern "C" void b200_set_error(const char *what, cudaError_t e, const char *file, int line);
+extern "C" void b200_count_launch(int n);
+
+// ---------------------------------------------------------------- reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum of NV values per thread; result valid in thread 0.
+// smem must hold NV * 32 doubles. All threads must call.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *smem) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  __syncthreads();  // protect smem reuse across consecutive calls
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) smem[i * 32 + wid] = v[i];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double t = (lane < nw) ? smem[i * 32 + lane] : 0.0;
+      v[i] = warp_sum(t);
+    }
+  }
+}
+template <int NV>
+__device__ __forceinline__ void block_max(double (&v)[NV], double *smem) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_max(v[i]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) smem[i * 32 + wid] = v[i];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double t = (lane < nw) ? smem[i * 32 + lane] : 0.0;  // all maxima here are of |.| >= 0
+      v[i] = warp_max(t);
+    }
+  }
+}
+
+// Grid-level finish. Thread 0 of each block holds `mine[0..NV)`; it publishes
+// them into partials[i * gridDim.x + blockIdx.x], then the last block to
+// arrive (ticket counter) reduces the slots in index order with warp 0 and
+// returns true in ALL threads of that block with the totals in thread 0's
+// `mine`. `is_max[i]` selects max instead of sum for value i (bitmask).
+// The counter is reset by the last block, so the buffer is reusable by the
+// next kernel on the same stream.
+template <int NV>
+__device__ __forceinline__ bool grid_finish(double (&mine)[NV], double *partials,
+                                            unsigned int *counter, unsigned max_mask,
+                                            double *smem) {
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) partials[i * gridDim.x + blockIdx.x] = mine[i];
+    __threadfence();
+    unsigned t = atomicAdd(counter, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  // fixed-order reduction of gridDim.x slots: thread t accumulates slots t, t+B, ...
+  double acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const bool mx = (max_mask >> i) & 1u;
+    double a = 0.0;
+    for (unsigned j = threadIdx.x; j < gridDim.x; j += blockDim.x) {
+      double p = __ldcg(&partials[i * gridDim.x + j]);
+      a = mx ? fmax(a, p) : a + p;
+    }
+    acc[i] = a;
+  }
+  // split by kind: run both reductions, pick per value
+  double s[NV], m[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { s[i] = acc[i]; m[i] = acc[i]; }
+  block_sum<NV>(s, smem);
+  block_max<NV>(m, smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) mine[i] = ((max_mask >> i) & 1u) ? m[i] : s[i];
+    *counter = 0u;
+    __threadfence();
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------- TMA / mbarrier (sm_100a)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// 1-D bulk async copy global -> shared, completion on mbarrier (bytes multiple of 16,
+// both addresses 16-byte aligned).
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, unsigned bytes,
+                                            uint64_t *bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}

@@ -1,0 +1,118 @@
+/* dev_api.h -- INTERNAL thin C layer between the C host code (host/ *.c) and the
+ * hand-written sm_100a kernels (kernels/ *.cu).  All pointers named d_* are
+ * device pointers; everything is enqueued on the library stream and is
+ * asynchronous unless stated otherwise.  Return value: 0 ok, <0 error
+ * (message via b200_last_error()). */
+#ifndef B200_DEV_API_H
+#define B200_DEV_API_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------ runtime ---- */
+int b200_runtime_init(void);           /* picks device (LOCAL_RANK / SCS_B200_DEVICE), creates stream */
+int b200_device_ok(void);
+const char *b200_last_error(void);
+int b200_num_sms(void);
+void *b200_stream(void);               /* cudaStream_t */
+void *b200_malloc(size_t bytes);       /* cudaMalloc, NULL on failure */
+void b200_free(void *d_p);
+void *b200_host_alloc(size_t bytes);   /* pinned host memory */
+void b200_host_free(void *p);
+int b200_h2d(void *d_dst, const void *src, size_t bytes);  /* async on stream (pageable => staged) */
+int b200_d2h(void *dst, const void *d_src, size_t bytes);  /* async on stream */
+int b200_d2d(void *d_dst, const void *d_src, size_t bytes);
+int b200_memset0(void *d_dst, size_t bytes);
+int b200_sync(void);
+long long b200_launches(void);
+/* CUDA-event timing on the library stream */
+int b200_timer_start(void);
+double b200_timer_stop_ms(void);       /* syncs; <0 on error */
+
+/* ------------------------------------------------------------ SpMV ------- */
+/* A sparse operator stored row-major (CSR): row r has entries
+ * [rowptr[r], rowptr[r+1]) with column indices colidx[] and values vals[].
+ * For SCS both orientations are used: the CSC arrays of A *are* the CSR of A'
+ * (reference linsys/scs_matrix.c:161-186 accum_by_atrans), and the explicit
+ * transpose At gives the CSR of A (reference cpu/indirect/private.c:7-46). */
+typedef struct B200Spmv B200Spmv;
+
+B200Spmv *b200_spmv_create(int nrows, int ncols, const int *h_rowptr, const int *h_colidx,
+                           const double *h_vals);
+void b200_spmv_destroy(B200Spmv *M);
+int b200_spmv_nrows(const B200Spmv *M);
+int b200_spmv_ncols(const B200Spmv *M);
+long long b200_spmv_nnz(const B200Spmv *M);
+const double *b200_spmv_vals(const B200Spmv *M);   /* device */
+const int *b200_spmv_colidx(const B200Spmv *M);    /* device */
+const int *b200_spmv_rowptr(const B200Spmv *M);    /* device */
+/* algorithmic bytes of one launch: 12 nnz + 4 (R+1) + 8 C + 8 R (+ 8 R per extra row vector) */
+double b200_spmv_alg_bytes(const B200Spmv *M, int extra_row_vectors);
+
+enum { B200_POST_NONE = 0, B200_POST_DIV = 1, B200_POST_FMA_DOT = 2, B200_POST_FMA = 3 };
+enum { B200_HOOK_NONE = 0, B200_HOOK_CG_ALPHA = 1 };
+
+typedef struct {
+  const double *d_x;     /* gather vector, length ncols */
+  double *d_y;           /* output, length nrows */
+  const double *d_init;  /* NULL: chain starts at 0; else at init_sign * d_init[r] (may alias d_y) */
+  double init_sign;
+  int post;              /* B200_POST_*: y = s | s / d[r] | fma(d[r], v[r], s) with dot(v, y) | same, no dot */
+  const double *d_d;
+  const double *d_v;
+  double *d_dot;         /* B200_POST_FMA_DOT: receives sum_r v[r]*y[r] */
+  int hook;              /* B200_HOOK_*: run by the last block after the dot is final */
+  void *d_hook_arg;      /* B200CgCtl* for B200_HOOK_CG_ALPHA */
+  const int *d_skip;     /* optional: kernel returns at once if *d_skip != 0 */
+} B200SpmvArgs;
+
+int b200_spmv(const B200Spmv *M, const B200SpmvArgs *a);
+
+/* ------------------------------------------------------------ CG --------- */
+/* Device-resident control block of one PCG solve (reference
+ * linsys/cpu/indirect/private.c:133-217). Lives in device memory; the host
+ * reads it back only to learn `done` / `iters`. */
+typedef struct {
+  double ztr, ztr_prev, alpha, beta, pGp, rnorm, tol, bnorm;
+  int iters;    /* CG iterations completed */
+  int done;     /* 1: converged / broke / hit max_its; kernels early-exit */
+  int max_its;
+  int skip;     /* 1: ||b||_inf <= 1e-12, whole solve is b := 0 */
+  int pad[4];
+} B200CgCtl;
+
+typedef struct {
+  int n, m;
+  const B200Spmv *A;   /* CSR of A  (m x n): rows of A   -> used for z = A p      */
+  const B200Spmv *At;  /* CSR of A' (n x m): cols of A   -> used for y = A' z     */
+  const B200Spmv *P;   /* full symmetric P as CSR (n x n) or NULL                 */
+  const double *d_rx;  /* R_x (n) */
+  const double *d_ry;  /* R_y (m) */
+  double *d_M;         /* Jacobi preconditioner (n) */
+  double *d_p, *d_r, *d_Gp, *d_z, *d_tmp; /* n, n, n, n, m */
+  B200CgCtl *d_ctl;
+  double *d_partials;  /* reduction slots */
+  unsigned int *d_counter;
+  B200CgCtl *h_ctl;    /* pinned mirror */
+} B200Cg;
+
+/* M_j = 1 / (R_x,j + P_jj + sum_k A_kj^2 / R_y,k)   (private.c:50-82) */
+int b200_cg_set_preconditioner(const B200Cg *cg, const double *d_Pdiag);
+/* Full device solve of [[R_x+P, A'],[A, -R_y]] [x;y] = b in place on d_b (n+m),
+ * warm start d_s (n) or NULL; returns CG iterations (>=0) or <0 on error.
+ * Synchronises with the host only to poll the done flag. (private.c:284-324) */
+int b200_cg_solve(B200Cg *cg, double *d_b, const double *d_s, double tol, int max_its,
+                  int its_hint, const double *d_tol /* optional device tol */);
+/* one CG iteration (4 kernels), for timing */
+int b200_cg_one_iteration(B200Cg *cg, double *d_x);
+double b200_cg_iter_alg_bytes(const B200Cg *cg);
+
+/* ------------------------------------------------------------ vector ops - */
+/* out = |a|_inf etc. are produced into device scalars; see admm.cu */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,321 @@
+/* linsys_b200.c -- the SCS linear-system plugin ("sparse-indirect B200") in C.
+ *
+ * Implements the five link-time symbols of reference include/linsys.h:25-71 on
+ * top of the device CG (kernels/cg.cu) and SpMV (kernels/spmv.cu):
+ *
+ *   scs_init_lin_sys_work     <- reference cpu/indirect/private.c:225-270
+ *   scs_solve_lin_sys         <- :284-324
+ *   scs_update_lin_sys_diag_r <- :327-331
+ *   scs_free_lin_sys_work     <- :333-349
+ *   scs_get_lin_sys_method    <- :221-223
+ *
+ * plus device-pointer variants (b200_linsys_*_dev) used by the device-resident
+ * ADMM driver (host/scs_driver.c) so that the hot loop never crosses PCIe.
+ */
+#include "linsys_b200.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+const char *scs_get_lin_sys_method(void) { return "sparse-indirect-b200-cuda"; }
+
+/* counting-sort transpose of a CSC matrix (m x n) into the CSC of its transpose
+ * (= CSR of the original). Entries of each output column keep ascending source
+ * column order, exactly like reference private.c:7-46, so that the per-row
+ * summation order of A x matches the reference's accum_by_atrans(At, ...). */
+static int transpose_csc(int m, int n, const int *Ap, const int *Ai, const double *Ax, int **Cp_out,
+                         int **Ci_out, double **Cx_out) {
+  const int nnz = Ap[n];
+  int *Cp = (int *)calloc((size_t)m + 1, sizeof(int));
+  int *Ci = (int *)malloc(((size_t)nnz + 1) * sizeof(int));
+  double *Cx = (double *)malloc(((size_t)nnz + 1) * sizeof(double));
+  int *z = (int *)calloc((size_t)m + 1, sizeof(int));
+  int i, j, k;
+  if (!Cp || !Ci || !Cx || !z) {
+    free(Cp); free(Ci); free(Cx); free(z);
+    return -1;
+  }
+  for (k = 0; k < nnz; ++k) z[Ai[k]]++;
+  Cp[0] = 0;
+  for (i = 0; i < m; ++i) Cp[i + 1] = Cp[i] + z[i];
+  for (i = 0; i < m; ++i) z[i] = Cp[i];
+  for (j = 0; j < n; ++j) {
+    for (k = Ap[j]; k < Ap[j + 1]; ++k) {
+      const int q = z[Ai[k]]++;
+      Ci[q] = j;
+      Cx[q] = Ax[k];
+    }
+  }
+  free(z);
+  *Cp_out = Cp; *Ci_out = Ci; *Cx_out = Cx;
+  return 0;
+}
+
+/* expand upper-triangular CSC P into the full symmetric matrix in CSR
+ * (reference gpu/indirect/private.c:174-202 does the same for cuSPARSE);
+ * also extracts diag(P) for the preconditioner. */
+static int expand_sym_upper(int n, const int *Pp, const int *Pi, const double *Px, int **Fp_out,
+                            int **Fi_out, double **Fx_out, double *diag) {
+  const int nnz = Pp[n];
+  int *cnt = (int *)calloc((size_t)n + 1, sizeof(int));
+  int *Fp = (int *)calloc((size_t)n + 1, sizeof(int));
+  int *Fi;
+  double *Fx;
+  int i, j, k, tot = 0;
+  if (!cnt || !Fp) { free(cnt); free(Fp); return -1; }
+  for (j = 0; j < n; ++j) diag[j] = 0.0;
+  for (j = 0; j < n; ++j)
+    for (k = Pp[j]; k < Pp[j + 1]; ++k) {
+      i = Pi[k];
+      cnt[i]++;              /* entry (i,j) goes to row i */
+      if (i != j) cnt[j]++;  /* mirrored entry (j,i) goes to row j */
+      else diag[j] += Px[k];
+    }
+  for (i = 0; i < n; ++i) { Fp[i + 1] = Fp[i] + cnt[i]; }
+  tot = Fp[n];
+  Fi = (int *)malloc(((size_t)tot + 1) * sizeof(int));
+  Fx = (double *)malloc(((size_t)tot + 1) * sizeof(double));
+  if (!Fi || !Fx) { free(cnt); free(Fp); free(Fi); free(Fx); return -1; }
+  for (i = 0; i < n; ++i) cnt[i] = Fp[i];
+  /* rows get their entries in ascending column order: first the lower part
+   * (mirrors, columns < row) then the upper part. Two passes keep it sorted. */
+  for (j = 0; j < n; ++j)
+    for (k = Pp[j]; k < Pp[j + 1]; ++k) {
+      i = Pi[k];
+      if (i != j) { /* (i,j) with i<j stored; mirror (j,i): row j, col i < j */
+        const int q = cnt[j]++;
+        Fi[q] = i; Fx[q] = Px[k];
+      }
+    }
+  for (j = 0; j < n; ++j)
+    for (k = Pp[j]; k < Pp[j + 1]; ++k) {
+      i = Pi[k];
+      { const int q = cnt[i]++; Fi[q] = j; Fx[q] = Px[k]; } /* row i, col j >= i */
+    }
+  (void)nnz;
+  free(cnt);
+  *Fp_out = Fp; *Fi_out = Fi; *Fx_out = Fx;
+  return 0;
+}
+
+ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
+                                     const scs_float *diag_r) {
+  ScsLinSysWork *w;
+  int *Tp = NULL, *Ti = NULL;
+  double *Tx = NULL;
+  const int n = A->n, m = A->m;
+  if (b200_runtime_init() != 0) {
+    fprintf(stderr, "scs_b200: no usable sm_100 device: %s\n", b200_last_error());
+    return SCS_NULL;
+  }
+  w = (ScsLinSysWork *)calloc(1, sizeof(ScsLinSysWork));
+  if (!w) return SCS_NULL;
+  w->n = n; w->m = m;
+  w->nnz = A->p[n];
+  /* CSR of A' is the CSC of A as given */
+  w->At = b200_spmv_create(n, m, A->p, A->i, A->x);
+  if (transpose_csc(m, n, A->p, A->i, A->x, &Tp, &Ti, &Tx) != 0) goto fail;
+  w->A = b200_spmv_create(m, n, Tp, Ti, Tx);
+  free(Tp); free(Ti); free(Tx);
+  if (!w->A || !w->At) goto fail;
+  if (P) {
+    int *Fp = NULL, *Fi = NULL;
+    double *Fx = NULL;
+    double *diag = (double *)malloc((size_t)n * sizeof(double));
+    if (!diag || expand_sym_upper(n, P->p, P->i, P->x, &Fp, &Fi, &Fx, diag) != 0) {
+      free(diag);
+      goto fail;
+    }
+    w->P = b200_spmv_create(n, n, Fp, Fi, Fx);
+    w->d_Pdiag = (double *)b200_malloc((size_t)n * 8);
+    if (w->d_Pdiag) b200_h2d(w->d_Pdiag, diag, (size_t)n * 8);
+    free(Fp); free(Fi); free(Fx); free(diag);
+    if (!w->P || !w->d_Pdiag) goto fail;
+  }
+  w->d_diag_r = (double *)b200_malloc(((size_t)n + m + 1) * 8);
+  w->d_b = (double *)b200_malloc(((size_t)n + m) * 8);
+  w->d_s = (double *)b200_malloc((size_t)n * 8);
+  w->cg.d_M = (double *)b200_malloc((size_t)n * 8);
+  w->cg.d_p = (double *)b200_malloc((size_t)n * 8);
+  w->cg.d_r = (double *)b200_malloc((size_t)n * 8);
+  w->cg.d_Gp = (double *)b200_malloc((size_t)n * 8);
+  w->cg.d_z = (double *)b200_malloc((size_t)n * 8);
+  w->cg.d_tmp = (double *)b200_malloc((size_t)m * 8);
+  w->cg.d_ctl = (B200CgCtl *)b200_malloc(sizeof(B200CgCtl));
+  w->cg.d_partials = (double *)b200_malloc(4 * 2048 * 8);
+  w->cg.d_counter = (unsigned int *)b200_malloc(64);
+  w->cg.h_ctl = (B200CgCtl *)b200_host_alloc(sizeof(B200CgCtl));
+  if (!w->d_diag_r || !w->d_b || !w->d_s || !w->cg.d_M || !w->cg.d_p || !w->cg.d_r ||
+      !w->cg.d_Gp || !w->cg.d_z || !w->cg.d_tmp || !w->cg.d_ctl || !w->cg.d_partials ||
+      !w->cg.d_counter || !w->cg.h_ctl)
+    goto fail;
+  b200_memset0(w->cg.d_counter, 64);
+  b200_memset0(w->cg.d_ctl, sizeof(B200CgCtl));
+  memset(w->cg.h_ctl, 0, sizeof(B200CgCtl));
+  w->cg.n = n; w->cg.m = m;
+  w->cg.A = w->A; w->cg.At = w->At; w->cg.P = w->P;
+  w->cg.d_rx = w->d_diag_r;
+  w->cg.d_ry = w->d_diag_r + n;
+  if (b200_h2d(w->d_diag_r, diag_r, ((size_t)n + m) * 8) != 0) goto fail;
+  if (b200_cg_set_preconditioner(&w->cg, w->d_Pdiag) != 0) goto fail;
+  if (b200_sync() != 0) goto fail;
+  return w;
+fail:
+  fprintf(stderr, "scs_b200: init_lin_sys_work failed: %s\n", b200_last_error());
+  scs_free_lin_sys_work(w);
+  return SCS_NULL;
+}
+
+void scs_free_lin_sys_work(ScsLinSysWork *w) {
+  if (!w) return;
+  b200_sync();
+  b200_spmv_destroy(w->A);
+  b200_spmv_destroy(w->At);
+  b200_spmv_destroy(w->P);
+  b200_free(w->d_Pdiag);
+  b200_free(w->d_diag_r);
+  b200_free(w->d_b);
+  b200_free(w->d_s);
+  b200_free(w->cg.d_M);
+  b200_free(w->cg.d_p);
+  b200_free(w->cg.d_r);
+  b200_free(w->cg.d_Gp);
+  b200_free(w->cg.d_z);
+  b200_free(w->cg.d_tmp);
+  b200_free(w->cg.d_ctl);
+  b200_free(w->cg.d_partials);
+  b200_free(w->cg.d_counter);
+  b200_host_free(w->cg.h_ctl);
+  free(w);
+}
+
+/* device-pointer solve used by the ADMM driver; d_tol optional device scalar */
+int b200_linsys_solve_dev(ScsLinSysWork *w, double *d_b, const double *d_s, double tol,
+                          const double *d_tol) {
+  long long max_its = 10LL * w->n; /* reference private.c:307 */
+  int its;
+  if (max_its > 2000000000LL) max_its = 2000000000LL;
+  its = b200_cg_solve(&w->cg, d_b, d_s, tol, (int)max_its, w->last_cg_its, d_tol);
+  if (its < 0) return -1;
+  w->last_cg_its = its;
+  w->tot_cg_its += its;
+  w->n_solves += 1;
+  return 0;
+}
+
+int b200_linsys_update_diag_r_dev(ScsLinSysWork *w, const double *d_diag_r) {
+  if (d_diag_r != w->d_diag_r) {
+    if (b200_d2d(w->d_diag_r, d_diag_r, ((size_t)w->n + w->m) * 8) != 0) return -1;
+  }
+  return b200_cg_set_preconditioner(&w->cg, w->d_Pdiag);
+}
+
+scs_int scs_solve_lin_sys(ScsLinSysWork *w, scs_float *b, const scs_float *s, scs_float tol) {
+  const size_t nm = (size_t)w->n + w->m;
+  if (tol <= 0.) {
+    fprintf(stderr, "Warning: tol = %4f <= 0, likely compiled without setting INDIRECT flag.\n",
+            tol);
+  }
+  if (b200_h2d(w->d_b, b, nm * 8) != 0) return -1;
+  if (s && b200_h2d(w->d_s, s, (size_t)w->n * 8) != 0) return -1;
+  if (b200_linsys_solve_dev(w, w->d_b, s ? w->d_s : NULL, tol, NULL) != 0) return -1;
+  if (b200_d2h(b, w->d_b, nm * 8) != 0) return -1;
+  if (b200_sync() != 0) return -1;
+  return 0;
+}
+
+scs_int scs_update_lin_sys_diag_r(ScsLinSysWork *w, const scs_float *new_diag_r) {
+  if (b200_h2d(w->d_diag_r, new_diag_r, ((size_t)w->n + w->m) * 8) != 0) return -1;
+  if (b200_linsys_update_diag_r_dev(w, w->d_diag_r) != 0) return -1;
+  return b200_sync() == 0 ? 0 : -1;
+}
+
+scs_int scs_b200_linsys_last_cg_its(const ScsLinSysWork *w) { return w->last_cg_its; }
+long long scs_b200_linsys_total_cg_its(const ScsLinSysWork *w) { return w->tot_cg_its; }
+
+static scs_int accum_generic(ScsLinSysWork *w, const B200Spmv *M, int ncols, int nrows,
+                             const scs_float *x, scs_float *y, scs_int accumulate) {
+  B200SpmvArgs a;
+  double *d_x = (double *)b200_malloc((size_t)ncols * 8);
+  double *d_y = (double *)b200_malloc((size_t)nrows * 8);
+  int rc = -1;
+  (void)w;
+  if (!d_x || !d_y) goto out;
+  if (b200_h2d(d_x, x, (size_t)ncols * 8) != 0) goto out;
+  if (accumulate && b200_h2d(d_y, y, (size_t)nrows * 8) != 0) goto out;
+  memset(&a, 0, sizeof(a));
+  a.d_x = d_x; a.d_y = d_y; a.d_init = accumulate ? d_y : NULL; a.init_sign = 1.0;
+  a.post = B200_POST_NONE; a.hook = B200_HOOK_NONE;
+  if (b200_spmv(M, &a) != 0) goto out;
+  if (b200_d2h(y, d_y, (size_t)nrows * 8) != 0) goto out;
+  if (b200_sync() != 0) goto out;
+  rc = 0;
+out:
+  b200_free(d_x);
+  b200_free(d_y);
+  return rc;
+}
+
+scs_int scs_b200_accum_by_a(ScsLinSysWork *w, const scs_float *x, scs_float *y,
+                            scs_int accumulate) {
+  return accum_generic(w, w->A, w->n, w->m, x, y, accumulate);
+}
+scs_int scs_b200_accum_by_atrans(ScsLinSysWork *w, const scs_float *x, scs_float *y,
+                                 scs_int accumulate) {
+  return accum_generic(w, w->At, w->m, w->n, x, y, accumulate);
+}
+
+/* --- device timing helpers for bench.py (inputs resident in HBM) --------- */
+double scs_b200_time_spmv(ScsLinSysWork *w, scs_int op, scs_int reps, double *alg_bytes) {
+  const B200Spmv *M = op == 0 ? w->A : w->At;
+  const int ncols = b200_spmv_ncols(M), nrows = b200_spmv_nrows(M);
+  B200SpmvArgs a;
+  double ms = -1.0;
+  int i;
+  double *d_x = (double *)b200_malloc((size_t)ncols * 8);
+  double *d_y = (double *)b200_malloc((size_t)nrows * 8);
+  double *hx = (double *)malloc((size_t)ncols * 8);
+  if (!d_x || !d_y || !hx) goto out;
+  for (i = 0; i < ncols; ++i) hx[i] = 1.0 + 1e-3 * (double)(i % 1000);
+  if (b200_h2d(d_x, hx, (size_t)ncols * 8) != 0) goto out;
+  memset(&a, 0, sizeof(a));
+  a.d_x = d_x; a.d_y = d_y; a.init_sign = 1.0; a.post = B200_POST_NONE;
+  for (i = 0; i < 3; ++i) if (b200_spmv(M, &a) != 0) goto out;
+  if (b200_sync() != 0) goto out;
+  if (b200_timer_start() != 0) goto out;
+  for (i = 0; i < reps; ++i) if (b200_spmv(M, &a) != 0) goto out;
+  ms = b200_timer_stop_ms();
+  if (ms >= 0) ms /= (double)reps;
+  if (alg_bytes) *alg_bytes = b200_spmv_alg_bytes(M, 0);
+out:
+  b200_free(d_x); b200_free(d_y); free(hx);
+  return ms;
+}
+
+double scs_b200_time_cg_iter(ScsLinSysWork *w, scs_int reps, double *alg_bytes) {
+  /* run `reps` genuine CG iterations on a synthetic rhs with the stop test
+   * disabled (tol = 0 never satisfies ||r|| < tol) and time them on the stream */
+  const size_t nm = (size_t)w->n + w->m;
+  double *hb = (double *)malloc(nm * 8);
+  double ms = -1.0;
+  size_t i;
+  int k;
+  if (!hb) return -1.0;
+  for (i = 0; i < nm; ++i) hb[i] = 0.5 + 1e-3 * (double)(i % 997);
+  if (b200_h2d(w->d_b, hb, nm * 8) != 0) goto out;
+  /* set up p, r, z, ctl with a 1-iteration solve, then time raw iterations */
+  if (b200_cg_solve(&w->cg, w->d_b, NULL, 0.0, 1, 0, NULL) < 0) goto out;
+  w->cg.h_ctl->done = 0;
+  w->cg.h_ctl->max_its = 2000000000;
+  if (b200_h2d(w->cg.d_ctl, w->cg.h_ctl, sizeof(B200CgCtl)) != 0) goto out;
+  for (k = 0; k < 3; ++k) if (b200_cg_one_iteration(&w->cg, w->d_b) != 0) goto out;
+  if (b200_sync() != 0) goto out;
+  if (b200_timer_start() != 0) goto out;
+  for (k = 0; k < reps; ++k) if (b200_cg_one_iteration(&w->cg, w->d_b) != 0) goto out;
+  ms = b200_timer_stop_ms();
+  if (ms >= 0) ms /= (double)reps;
+  if (alg_bytes) *alg_bytes = b200_cg_iter_alg_bytes(&w->cg);
+out:
+  free(hb);
+  return ms;
+}

@@ -1,0 +1,30 @@
+/* linsys_b200.h -- private definition of struct SCS_LIN_SYS_WORK for the B200
+ * backend (the reference keeps one such private.h per backend, e.g.
+ * linsys/cpu/indirect/private.h:16-31). */
+#ifndef LINSYS_B200_H
+#define LINSYS_B200_H
+#include "../../../include/scs_b200.h"
+#include "../dev_api.h"
+
+struct SCS_LIN_SYS_WORK {
+  int n, m;
+  long long nnz;
+  B200Spmv *A;      /* CSR of A  (rows of A; built by transposing the CSC input) */
+  B200Spmv *At;     /* CSR of A' (= the CSC arrays of A as given) */
+  B200Spmv *P;      /* full symmetric P in CSR, or NULL */
+  double *d_Pdiag;  /* diag(P) (n) or NULL */
+  double *d_diag_r; /* device copy of [R_x; R_y] (n+m+1) */
+  double *d_b;      /* staging for the host-pointer plugin call (n+m) */
+  double *d_s;      /* staging for the warm start (n) */
+  B200Cg cg;
+  int last_cg_its;
+  long long tot_cg_its;
+  long long n_solves;
+};
+
+/* device-pointer variants used by the ADMM driver */
+int b200_linsys_solve_dev(ScsLinSysWork *w, double *d_b, const double *d_s, double tol,
+                          const double *d_tol);
+int b200_linsys_update_diag_r_dev(ScsLinSysWork *w, const double *d_diag_r);
+
+#endif

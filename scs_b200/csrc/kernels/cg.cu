@@ -1,0 +1,304 @@
+// cg.cu -- device-resident Jacobi-preconditioned conjugate gradient for the SCS
+// reduced KKT system  (R_x + P + A' R_y^{-1} A) x = r_x + A' R_y^{-1} r_y,
+// y = R_y^{-1}(A x - r_y).
+//
+// Replaces reference linsys/cpu/indirect/private.c:50-82 (set_preconditioner),
+// :106-119 (mat_vec), :133-217 (pcg), :284-324 (scs_solve_lin_sys) and the
+// cuBLAS/cuSPARSE composition of linsys/gpu/indirect/private.c:364-527.
+//
+// The scalars alpha, beta, z'r, ||r||_inf and the stop decision never leave the
+// GPU: a control block (B200CgCtl) lives in device memory, the last block of
+// each reduction-carrying kernel updates it, and every kernel of the loop
+// returns at once when ctl->done is set.  The host enqueues CG iterations in
+// batches and polls `done` with one small async copy per batch.
+//
+// One CG iteration = 4 kernels:
+//   K1  tmp = R_y^{-1} (A p)                         spmv (CSR of A), POST_DIV
+//   K2  Gp  = R_x p + [P p] + A' tmp ;  p'Gp ; alpha spmv (CSR of A'), POST_FMA_DOT + hook
+//   K3  x += alpha p; r -= alpha Gp; z = M r; z'r, ||r||_inf; stop test; beta
+//   K4  p = z + beta p
+// Algorithmic bytes: 24 nnz + 4 (m+n+2) + 24 m + 120 n   (DESIGN.md).
+#include "../common.cuh"
+#include "../dev_api.h"
+#include <math.h>
+
+#define VEC_THREADS B200_RED_THREADS
+
+static inline int vec_grid(long long n) {
+  long long g = (n + (long long)VEC_THREADS * 4 - 1) / ((long long)VEC_THREADS * 4);
+  long long cap = 4LL * b200_num_sms();
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ---------------------------------------------------------------------------
+// M_j = 1 / (R_x,j + sum_k A_kj^2 / R_y,row(k) + P_jj), same accumulation order
+// as the reference loop (private.c:61-78). One thread per column of A.
+__global__ void k_set_preconditioner(int n, const int *__restrict__ colptr,
+                                     const int *__restrict__ rowidx, const double *__restrict__ vals,
+                                     const double *__restrict__ rx, const double *__restrict__ ry,
+                                     const double *__restrict__ pdiag, double *__restrict__ M) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    double acc = rx[j];
+    const int a = colptr[j], b = colptr[j + 1];
+    for (int k = a; k < b; ++k) {
+      const double v = vals[k];
+      acc += v * v / ry[rowidx[k]];
+    }
+    if (pdiag != nullptr) acc += pdiag[j];
+    M[j] = 1.0 / acc;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Prologue: bnorm = ||b||_inf over n+m, tmp = r_y ./ R_y, control block reset.
+// (private.c:296-303)
+__global__ void __launch_bounds__(VEC_THREADS)
+k_cg_prepare(int n, int m, const double *__restrict__ b, const double *__restrict__ ry,
+             double *__restrict__ tmp, B200CgCtl *ctl, double tol, const double *d_tol, int max_its,
+             double *partials, unsigned int *counter) {
+  __shared__ double s_red[64];
+  double mx[1] = {0.0};
+  const long long tot = (long long)n + m;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < tot;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double v = b[i];
+    mx[0] = fmax(mx[0], fabs(v));
+    if (i >= n) tmp[i - n] = v / ry[i - n];
+  }
+  block_max<1>(mx, s_red);
+  if (grid_finish<1>(mx, partials, counter, 1u, s_red)) {
+    if (threadIdx.x == 0) {
+      const double t = (d_tol != nullptr) ? *d_tol : tol;
+      ctl->bnorm = mx[0];
+      ctl->tol = t;
+      ctl->skip = (mx[0] <= 1e-12) ? 1 : 0;  // NaN compares false -> not skipped, like the reference
+      ctl->done = ctl->skip;
+      ctl->iters = 0;
+      ctl->max_its = max_its;
+      ctl->ztr = 0.0;
+      ctl->ztr_prev = 0.0;
+      ctl->alpha = 0.0;
+      ctl->beta = 0.0;
+      ctl->rnorm = 0.0;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// CG start (private.c:145-172). warm==0: r = b, x = 0.  warm==1: Gs is in r;
+// r = -(Gs - b) ; x = s.  Then ||r||_inf test, z = M r, ztr = z'r, p = z.
+__global__ void __launch_bounds__(VEC_THREADS)
+k_cg_init(int n, int warm, double *__restrict__ x /* b[0:n] */, const double *__restrict__ s,
+          double *__restrict__ r, const double *__restrict__ M, double *__restrict__ z,
+          double *__restrict__ p, B200CgCtl *ctl, double *partials, unsigned int *counter) {
+  if (ctl->skip) return;
+  __shared__ double s_red[128];
+  double acc[2] = {0.0, 0.0};  // [0] = z'r (sum), [1] = ||r||_inf (max)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double ri;
+    if (warm) {
+      double t = r[i];
+      t += -1.0 * x[i];
+      ri = -t;
+      x[i] = s[i];
+    } else {
+      ri = x[i];
+      x[i] = 0.0;
+    }
+    r[i] = ri;
+    const double zi = ri * M[i];
+    z[i] = zi;
+    p[i] = zi;
+    acc[0] = fma(zi, ri, acc[0]);
+    acc[1] = fmax(acc[1], fabs(ri));
+  }
+  double sm[1] = {acc[0]}, mx[1] = {acc[1]};
+  block_sum<1>(sm, s_red);
+  block_max<1>(mx, s_red + 64);
+  double both[2] = {sm[0], mx[0]};
+  if (grid_finish<2>(both, partials, counter, 2u, s_red)) {
+    if (threadIdx.x == 0) {
+      ctl->ztr = both[0];
+      ctl->rnorm = both[1];
+      if (both[1] < fmax(ctl->tol, 1e-12)) ctl->done = 1;
+      if (ctl->max_its <= 0) ctl->done = 1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K3 (private.c:181-211): x += alpha p; r -= alpha Gp; z = M r; reductions.
+__global__ void __launch_bounds__(VEC_THREADS)
+k_cg_update(int n, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
+            const double *__restrict__ Gp, const double *__restrict__ M, double *__restrict__ z,
+            B200CgCtl *ctl, double *partials, unsigned int *counter) {
+  if (ctl->done) return;
+  __shared__ double s_red[128];
+  const double alpha = ctl->alpha;
+  const double nalpha = -alpha;
+  double acc0 = 0.0, acc1 = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    x[i] = fma(alpha, p[i], x[i]);
+    const double ri = fma(nalpha, Gp[i], r[i]);
+    r[i] = ri;
+    const double zi = ri * M[i];
+    z[i] = zi;
+    acc0 = fma(zi, ri, acc0);
+    acc1 = fmax(acc1, fabs(ri));
+  }
+  double sm[1] = {acc0}, mx[1] = {acc1};
+  block_sum<1>(sm, s_red);
+  block_max<1>(mx, s_red + 64);
+  double both[2] = {sm[0], mx[0]};
+  if (grid_finish<2>(both, partials, counter, 2u, s_red)) {
+    if (threadIdx.x == 0) {
+      const double ztr_prev = ctl->ztr;
+      ctl->ztr_prev = ztr_prev;
+      ctl->ztr = both[0];
+      ctl->rnorm = both[1];
+      ctl->iters += 1;
+      if (both[1] < ctl->tol) {
+        ctl->done = 1;
+      } else if (ztr_prev == 0.0) {
+        ctl->done = 1;
+      } else {
+        ctl->beta = both[0] / ztr_prev;
+        if (ctl->iters >= ctl->max_its) ctl->done = 1;
+      }
+    }
+  }
+}
+
+// K4 (private.c:212-214): p = z + beta p
+__global__ void __launch_bounds__(VEC_THREADS)
+k_cg_pupdate(int n, double *__restrict__ p, const double *__restrict__ z, const B200CgCtl *ctl) {
+  if (ctl->done) return;
+  const double beta = ctl->beta;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    p[i] = fma(beta, p[i], z[i]);
+}
+
+__global__ void k_zero_if(long long len, double *__restrict__ v, const int *flag) {
+  if (!*flag) return;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < len;
+       i += (long long)gridDim.x * blockDim.x)
+    v[i] = 0.0;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" int b200_cg_set_preconditioner(const B200Cg *cg, const double *d_Pdiag) {
+  cudaStream_t st = (cudaStream_t)b200_stream();
+  // CSR of A' == CSC of A: rowptr = column pointers, colidx = row indices
+  k_set_preconditioner<<<vec_grid(cg->n), 256, 0, st>>>(
+      cg->n, b200_spmv_rowptr(cg->At), b200_spmv_colidx(cg->At), b200_spmv_vals(cg->At), cg->d_rx,
+      cg->d_ry, d_Pdiag, cg->d_M);
+  b200_count_launch(1);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// y = (R_x + P + A' R_y^-1 A) x   (private.c:106-119); dot/hook optional
+static int mat_vec(B200Cg *cg, const double *d_x, double *d_y, int with_dot, const int *d_skip) {
+  B200SpmvArgs a;
+  // K1: tmp = (A x) ./ R_y
+  a.d_x = d_x; a.d_y = cg->d_tmp; a.d_init = nullptr; a.init_sign = 1.0;
+  a.post = B200_POST_DIV; a.d_d = cg->d_ry; a.d_v = nullptr; a.d_dot = nullptr;
+  a.hook = B200_HOOK_NONE; a.d_hook_arg = nullptr; a.d_skip = d_skip;
+  if (b200_spmv(cg->A, &a) != 0) return -1;
+  const double *init = nullptr;
+  if (cg->P) {
+    // y = P x first (reference accumulates P x before A' z)
+    a.d_x = d_x; a.d_y = d_y; a.d_init = nullptr; a.post = B200_POST_NONE;
+    a.d_d = nullptr; a.d_v = nullptr;
+    if (b200_spmv(cg->P, &a) != 0) return -1;
+    init = d_y;
+  }
+  // K2: y = fma(R_x, x, init + A' tmp)
+  a.d_x = cg->d_tmp; a.d_y = d_y; a.d_init = init; a.init_sign = 1.0;
+  a.post = with_dot ? B200_POST_FMA_DOT : B200_POST_FMA;
+  a.d_d = cg->d_rx; a.d_v = d_x; a.d_dot = with_dot ? &cg->d_ctl->pGp : nullptr;
+  a.hook = with_dot ? B200_HOOK_CG_ALPHA : B200_HOOK_NONE;
+  a.d_hook_arg = cg->d_ctl; a.d_skip = d_skip;
+  return b200_spmv(cg->At, &a);
+}
+
+static int cg_iteration(B200Cg *cg, double *d_x) {
+  cudaStream_t st = (cudaStream_t)b200_stream();
+  const int n = cg->n;
+  const int g = vec_grid(n);
+  if (mat_vec(cg, cg->d_p, cg->d_Gp, 1, &cg->d_ctl->done) != 0) return -1;
+  k_cg_update<<<g, VEC_THREADS, 0, st>>>(n, d_x, cg->d_r, cg->d_p, cg->d_Gp, cg->d_M, cg->d_z,
+                                         cg->d_ctl, cg->d_partials, cg->d_counter);
+  k_cg_pupdate<<<g, VEC_THREADS, 0, st>>>(n, cg->d_p, cg->d_z, cg->d_ctl);
+  b200_count_launch(2);
+  return 0;
+}
+
+extern "C" int b200_cg_one_iteration(B200Cg *cg, double *d_x) { return cg_iteration(cg, d_x); }
+
+extern "C" double b200_cg_iter_alg_bytes(const B200Cg *cg) {
+  const double nnz = (double)b200_spmv_nnz(cg->A);
+  return 24.0 * nnz + 4.0 * (cg->m + cg->n + 2.0) + 24.0 * cg->m + 120.0 * cg->n;
+}
+
+extern "C" int b200_cg_solve(B200Cg *cg, double *d_b, const double *d_s, double tol, int max_its,
+                             int its_hint, const double *d_tol) {
+  cudaStream_t st = (cudaStream_t)b200_stream();
+  const int n = cg->n, m = cg->m;
+  const int g = vec_grid(n);
+  const int *d_skip = &cg->d_ctl->skip;
+
+  // prologue: ||b||, tmp = r_y / R_y
+  k_cg_prepare<<<vec_grid((long long)n + m), VEC_THREADS, 0, st>>>(
+      n, m, d_b, cg->d_ry, cg->d_tmp, cg->d_ctl, tol, d_tol, max_its, cg->d_partials,
+      cg->d_counter);
+  b200_count_launch(1);
+  // b[0:n] += A' tmp   (private.c:305)
+  {
+    B200SpmvArgs a;
+    a.d_x = cg->d_tmp; a.d_y = d_b; a.d_init = d_b; a.init_sign = 1.0; a.post = B200_POST_NONE;
+    a.d_d = nullptr; a.d_v = nullptr; a.d_dot = nullptr; a.hook = B200_HOOK_NONE;
+    a.d_hook_arg = nullptr; a.d_skip = d_skip;
+    if (b200_spmv(cg->At, &a) != 0) return -1;
+  }
+  // r = G s (warm) ; start
+  if (d_s != nullptr) {
+    if (mat_vec(cg, d_s, cg->d_r, 0, d_skip) != 0) return -1;
+  }
+  k_cg_init<<<g, VEC_THREADS, 0, st>>>(n, d_s != nullptr ? 1 : 0, d_b, d_s, cg->d_r, cg->d_M,
+                                       cg->d_z, cg->d_p, cg->d_ctl, cg->d_partials, cg->d_counter);
+  b200_count_launch(1);
+  CUDA_OK(cudaGetLastError());
+
+  // main loop in batches
+  int batch = its_hint + 2;
+  if (batch < 4) batch = 4;
+  if (batch > 96) batch = 96;
+  long long enq = 0;
+  for (;;) {
+    for (int i = 0; i < batch; ++i)
+      if (cg_iteration(cg, d_b) != 0) return -1;
+    enq += batch;
+    CUDA_OK(cudaMemcpyAsync(cg->h_ctl, cg->d_ctl, sizeof(B200CgCtl), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    if (cg->h_ctl->done) break;
+    if (enq >= (long long)max_its + 1) break;  // safety; device sets done at max_its
+    batch = batch < 16 ? 16 : (batch < 64 ? batch * 2 : 64);
+  }
+  // y = R_y^{-1} (A x - r_y)   (private.c:313-317)
+  {
+    B200SpmvArgs a;
+    a.d_x = d_b; a.d_y = d_b + n; a.d_init = d_b + n; a.init_sign = -1.0; a.post = B200_POST_DIV;
+    a.d_d = cg->d_ry; a.d_v = nullptr; a.d_dot = nullptr; a.hook = B200_HOOK_NONE;
+    a.d_hook_arg = nullptr; a.d_skip = d_skip;
+    if (b200_spmv(cg->A, &a) != 0) return -1;
+  }
+  if (cg->h_ctl->skip) {
+    k_zero_if<<<vec_grid((long long)n + m), 256, 0, st>>>((long long)n + m, d_b, d_skip);
+    b200_count_launch(1);
+  }
+  CUDA_OK(cudaGetLastError());
+  return cg->h_ctl->iters;
+}

@@ -1,0 +1,413 @@
+// spmv.cu -- fp64 / int32 sparse mat-vec for the SCS indirect KKT solve, sm_100a.
+//
+// Replaces reference linsys/scs_matrix.c:161-186 (accum_by_atrans, used for both
+// A'x on the CSC arrays and A x on the explicit transpose) and the cuSPARSE
+// calls of linsys/gpu/gpu.c:3-58.
+//
+// Design ("CSR-stream" on TMA):
+//   * the nonzeros are cut into TILES of consecutive whole rows holding at most
+//     tile_nnz (<=2048) entries; a row longer than a tile is cut into chunks
+//     that stay on one CTA (running carry);
+//   * each CTA owns a contiguous, weight-balanced range of tiles (static
+//     partition => no atomics, bit-reproducible) and walks it with a 3-stage
+//     ring: one elected thread issues 1-D TMA bulk copies (cp.async.bulk,
+//     L2 evict_first) of the tile's value and column-index slices into shared
+//     memory, completion signalled on an mbarrier;
+//   * phase 1: all threads gather x[col] for the tile's entries (coalesced reads
+//     of idx from smem, up to 4 independent 8-byte gathers per thread in flight);
+//   * phase 2: L lanes per row (L=1 for short rows) run the FMA chain over the
+//     row's (val, x) pairs from shared memory IN STORAGE ORDER -- for L=1 this is
+//     the same sequential fma chain the reference's scalar loop performs, so the
+//     result is bit-identical to the CPU; L>1 finishes with a fixed xor-shuffle
+//     tree;
+//   * fused epilogues: y = s | s / d[r] | fma(d[r], v[r], s) plus the dot
+//     product v'y with a deterministic last-block reduction and an optional
+//     hook that turns the dot into the CG step length on the device.
+//
+// Algorithmic bytes per launch: 12*nnz + 4*(R+1) + 8*C + 8*R (+8*R per
+// extra row vector read by the epilogue).
+#include "../common.cuh"
+#include "../dev_api.h"
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#define SPMV_THREADS 512
+#define SPMV_STAGES 3
+#define SPMV_TILE_NNZ 2048
+#define SPMV_TILE_CAP (SPMV_TILE_NNZ + 8)
+#define SPMV_TILE_ROWS 2048
+
+// tile descriptor: x=row0, y=nrows | (type<<28) | (lg_lanes<<24), z=k0, w=nnz
+#define TILE_NORMAL 0
+#define TILE_LONG_FIRST 1
+#define TILE_LONG_MID 2
+#define TILE_LONG_LAST 3
+#define TILE_LONG_ONLY 4  // single chunk (cannot happen by construction, kept for safety)
+
+struct B200Spmv {
+  int nrows, ncols;
+  long long nnz;
+  int *d_rowptr;
+  int *d_colidx;
+  double *d_vals;
+  int4 *d_tiles;
+  int *d_cta_tile_begin;
+  int ntiles;
+  int grid;
+  int tile_nnz;
+  double *d_partials;
+  unsigned int *d_counter;
+};
+
+static size_t spmv_smem_bytes() {
+  return (size_t)SPMV_STAGES * SPMV_TILE_CAP * 8 + (size_t)SPMV_TILE_NNZ * 8 +
+         (size_t)SPMV_STAGES * SPMV_TILE_CAP * 4 + SPMV_STAGES * 8 + 64 * 8;
+}
+
+__device__ __forceinline__ void spmv_issue_tile(const int4 t, int stage, double *s_vals, int *s_idx,
+                                                uint64_t *s_bar, const double *__restrict__ vals,
+                                                const int *__restrict__ colidx, uint64_t pol) {
+  const int k0 = t.z, nnz = t.w;
+  const int ka = k0 & ~3;
+  const int cnt = (k0 + nnz - ka + 3) & ~3;
+  mbar_expect_tx(&s_bar[stage], (unsigned)cnt * 12u);
+  if (cnt > 0) {
+    tma_load_1d(s_vals + (size_t)stage * SPMV_TILE_CAP, vals + ka, (unsigned)cnt * 8u, &s_bar[stage], pol);
+    tma_load_1d(s_idx + (size_t)stage * SPMV_TILE_CAP, colidx + ka, (unsigned)cnt * 4u, &s_bar[stage], pol);
+  }
+}
+
+template <int POST>
+__device__ __forceinline__ double spmv_epilogue(double s, int row, double *__restrict__ y,
+                                                const double *__restrict__ d,
+                                                const double *__restrict__ v, double &dot_acc) {
+  double out = s;
+  if (POST == B200_POST_DIV) {
+    out = s / d[row];
+  } else if (POST == B200_POST_FMA_DOT) {
+    const double vr = v[row];
+    out = fma(d[row], vr, s);
+    dot_acc = fma(vr, out, dot_acc);
+  } else if (POST == B200_POST_FMA) {
+    out = fma(d[row], v[row], s);
+  }
+  y[row] = out;
+  return out;
+}
+
+template <int POST>
+__global__ void __launch_bounds__(SPMV_THREADS, 2)
+spmv_csr_stream_kernel(const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                       const double *__restrict__ vals, const int4 *__restrict__ tiles,
+                       const int *__restrict__ cta_tile_begin, const double *__restrict__ x,
+                       double *__restrict__ y, const double *init, double init_sign,
+                       const double *__restrict__ d, const double *__restrict__ v, double *dot_out,
+                       int hook, void *hook_arg, const int *skip, double *partials,
+                       unsigned int *counter) {
+  if (skip != nullptr && *((volatile const int *)skip) != 0) return;
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *s_vals = reinterpret_cast<double *>(smem_raw);
+  double *s_xg = s_vals + SPMV_STAGES * SPMV_TILE_CAP;
+  int *s_idx = reinterpret_cast<int *>(s_xg + SPMV_TILE_NNZ);
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_idx + SPMV_STAGES * SPMV_TILE_CAP);
+  double *s_red = reinterpret_cast<double *>(s_bar + SPMV_STAGES);
+
+  const int tid = threadIdx.x;
+  const int t_begin = cta_tile_begin[blockIdx.x];
+  const int nt = cta_tile_begin[blockIdx.x + 1] - t_begin;
+  uint64_t pol = 0;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < SPMV_STAGES; ++s) mbar_init(&s_bar[s], 1);
+    mbar_fence_init();
+    pol = l2_policy_evict_first();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const int pre = nt < SPMV_STAGES ? nt : SPMV_STAGES;
+    for (int s = 0; s < pre; ++s)
+      spmv_issue_tile(tiles[t_begin + s], s, s_vals, s_idx, s_bar, vals, colidx, pol);
+  }
+
+  double dot_acc = 0.0;
+  double carry = 0.0;  // long-row running sum (thread 0)
+
+  for (int i = 0; i < nt; ++i) {
+    const int st = i % SPMV_STAGES;
+    const unsigned par = (unsigned)((i / SPMV_STAGES) & 1);
+    const int4 t = tiles[t_begin + i];
+    const int row0 = t.x;
+    const int nrows = t.y & 0x00ffffff;
+    const int lg = (t.y >> 24) & 0xf;
+    const int type = (t.y >> 28) & 0x7;
+    const int k0 = t.z, nnz = t.w;
+    const int off = k0 - (k0 & ~3);
+    const double *__restrict__ tv = s_vals + (size_t)st * SPMV_TILE_CAP + off;
+    const int *__restrict__ ti = s_idx + (size_t)st * SPMV_TILE_CAP + off;
+
+    mbar_wait(&s_bar[st], par);
+
+    // ---- phase 1: gather x for every entry of the tile
+    {
+      int k = tid;
+#pragma unroll 4
+      for (; k < nnz; k += SPMV_THREADS) s_xg[k] = __ldg(&x[ti[k]]);
+    }
+    __syncthreads();
+
+    // ---- phase 2: per-row FMA chains
+    if (type == TILE_NORMAL) {
+      if (lg == 0) {
+        for (int r = tid; r < nrows; r += SPMV_THREADS) {
+          const int row = row0 + r;
+          const int a = __ldg(&rowptr[row]) - k0, b = __ldg(&rowptr[row + 1]) - k0;
+          double s = (init != nullptr) ? init_sign * init[row] : 0.0;
+          for (int k = a; k < b; ++k) s = fma(tv[k], s_xg[k], s);
+          spmv_epilogue<POST>(s, row, y, d, v, dot_acc);
+        }
+      } else {
+        const int L = 1 << lg;
+        const int group = tid >> lg, lig = tid & (L - 1), ngroups = SPMV_THREADS >> lg;
+        const int npass = (nrows + ngroups - 1) / ngroups;
+        for (int pass = 0; pass < npass; ++pass) {
+          const int r = pass * ngroups + group;
+          const bool valid = r < nrows;
+          const int row = row0 + (valid ? r : 0);
+          int a = 0, b = 0;
+          if (valid) {
+            a = __ldg(&rowptr[row]) - k0;
+            b = __ldg(&rowptr[row + 1]) - k0;
+          }
+          double s = 0.0;
+          for (int k = a + lig; k < b; k += L) s = fma(tv[k], s_xg[k], s);
+          for (int o = L >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (valid && lig == 0) {
+            if (init != nullptr) s += init_sign * init[row];
+            spmv_epilogue<POST>(s, row, y, d, v, dot_acc);
+          }
+        }
+      }
+    } else {
+      // chunk of one long row: whole block reduces, thread 0 carries across chunks
+      double part[1] = {0.0};
+      for (int k = tid; k < nnz; k += SPMV_THREADS) part[0] = fma(tv[k], s_xg[k], part[0]);
+      block_sum<1>(part, s_red);
+      if (tid == 0) {
+        if (type == TILE_LONG_FIRST || type == TILE_LONG_ONLY)
+          carry = (init != nullptr) ? init_sign * init[row0] : 0.0;
+        carry += part[0];
+        if (type == TILE_LONG_LAST || type == TILE_LONG_ONLY)
+          spmv_epilogue<POST>(carry, row0, y, d, v, dot_acc);
+      }
+    }
+    __syncthreads();  // stage st and s_xg are free again
+    if (tid == 0 && i + SPMV_STAGES < nt)
+      spmv_issue_tile(tiles[t_begin + i + SPMV_STAGES], st, s_vals, s_idx, s_bar, vals, colidx, pol);
+  }
+
+  if (POST == B200_POST_FMA_DOT) {
+    double acc[1] = {dot_acc};
+    block_sum<1>(acc, s_red);
+    if (grid_finish<1>(acc, partials, counter, 0u, s_red)) {
+      if (tid == 0) {
+        *dot_out = acc[0];
+        if (hook == B200_HOOK_CG_ALPHA) {
+          B200CgCtl *c = reinterpret_cast<B200CgCtl *>(hook_arg);
+          c->pGp = acc[0];
+          c->alpha = c->ztr / acc[0];
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host side
+static int lanes_log2_for(int max_row_nnz) {
+  if (max_row_nnz <= 16) return 0;
+  if (max_row_nnz <= 48) return 2;
+  if (max_row_nnz <= 160) return 3;
+  return 5;
+}
+
+extern "C" B200Spmv *b200_spmv_create(int nrows, int ncols, const int *h_rowptr,
+                                      const int *h_colidx, const double *h_vals) {
+  if (b200_runtime_init() != 0) return nullptr;
+  B200Spmv *M = (B200Spmv *)calloc(1, sizeof(B200Spmv));
+  if (!M) return nullptr;
+  M->nrows = nrows;
+  M->ncols = ncols;
+  M->nnz = h_rowptr[nrows];
+  const long long nnz = M->nnz;
+  const int nsm = b200_num_sms();
+
+  // tile size: full tiles for big matrices, smaller ones so that small matrices
+  // still spread over all SMs
+  long long want = nnz / (4LL * nsm);
+  int tile_nnz = 256;
+  while (tile_nnz < SPMV_TILE_NNZ && tile_nnz < want) tile_nnz <<= 1;
+  M->tile_nnz = tile_nnz;
+  const int tile_rows = SPMV_TILE_ROWS;
+
+  std::vector<int4> tiles;
+  tiles.reserve((size_t)(nnz / tile_nnz + nrows / tile_rows + 16));
+  std::vector<long long> weight;  // cumulative weight after each tile
+  int r = 0;
+  long long cumw = 0;
+  while (r < nrows) {
+    const int k0 = h_rowptr[r];
+    const int rn = h_rowptr[r + 1] - k0;
+    if (rn > tile_nnz) {
+      // long row: chunks of tile_nnz
+      int done = 0;
+      while (done < rn) {
+        int c = rn - done < tile_nnz ? rn - done : tile_nnz;
+        int type = (done == 0) ? TILE_LONG_FIRST : ((done + c == rn) ? TILE_LONG_LAST : TILE_LONG_MID);
+        int4 t;
+        t.x = r;
+        t.y = 1 | (type << 28);
+        t.z = k0 + done;
+        t.w = c;
+        tiles.push_back(t);
+        cumw += c + 64;
+        weight.push_back(cumw);
+        done += c;
+      }
+      r += 1;
+      continue;
+    }
+    int r1 = r, cnt = 0, mx = 0;
+    while (r1 < nrows && (r1 - r) < tile_rows) {
+      const int rr = h_rowptr[r1 + 1] - h_rowptr[r1];
+      if (rr > tile_nnz) break;           // next is a long row
+      if (cnt + rr > tile_nnz) break;     // tile full
+      cnt += rr;
+      if (rr > mx) mx = rr;
+      ++r1;
+    }
+    int4 t;
+    t.x = r;
+    t.y = (r1 - r) | (TILE_NORMAL << 28) | (lanes_log2_for(mx) << 24);
+    t.z = k0;
+    t.w = cnt;
+    tiles.push_back(t);
+    cumw += cnt + 2LL * (r1 - r) + 64;
+    weight.push_back(cumw);
+    r = r1;
+  }
+  M->ntiles = (int)tiles.size();
+  int grid = 2 * nsm;
+  if (grid > M->ntiles) grid = M->ntiles;
+  if (grid < 1) grid = 1;
+  M->grid = grid;
+  std::vector<int> begin(grid + 1, 0);
+  {
+    // balanced contiguous partition by cumulative weight; never split a long row
+    int t = 0;
+    for (int c = 1; c < grid; ++c) {
+      const long long target = (cumw * c) / grid;
+      while (t < M->ntiles && weight[t] <= target) ++t;
+      // weight[t-1] <= target < weight[t]; boundary AFTER tile t-1 => begin = t
+      int bnd = t;
+      while (bnd < M->ntiles) {
+        int type = (tiles[bnd].y >> 28) & 7;
+        if (type == TILE_LONG_MID || type == TILE_LONG_LAST) ++bnd; else break;
+      }
+      if (bnd < begin[c - 1]) bnd = begin[c - 1];
+      begin[c] = bnd;
+      if (t < bnd) t = bnd;
+    }
+    begin[grid] = M->ntiles;
+  }
+
+  const size_t pad_nnz = (size_t)((nnz + 3) & ~3LL) + 8;
+  M->d_rowptr = (int *)b200_malloc((size_t)(nrows + 1) * 4);
+  M->d_colidx = (int *)b200_malloc(pad_nnz * 4);
+  M->d_vals = (double *)b200_malloc(pad_nnz * 8);
+  M->d_tiles = (int4 *)b200_malloc((size_t)(M->ntiles > 0 ? M->ntiles : 1) * sizeof(int4));
+  M->d_cta_tile_begin = (int *)b200_malloc((size_t)(grid + 1) * 4);
+  M->d_partials = (double *)b200_malloc((size_t)B200_MAX_PARTIALS * 8);
+  M->d_counter = (unsigned int *)b200_malloc(64);
+  if (!M->d_rowptr || !M->d_colidx || !M->d_vals || !M->d_tiles || !M->d_cta_tile_begin ||
+      !M->d_partials || !M->d_counter) {
+    b200_spmv_destroy(M);
+    return nullptr;
+  }
+  int rc = 0;
+  rc |= b200_memset0(M->d_colidx, pad_nnz * 4);
+  rc |= b200_memset0(M->d_vals, pad_nnz * 8);
+  rc |= b200_memset0(M->d_counter, 64);
+  rc |= b200_h2d(M->d_rowptr, h_rowptr, (size_t)(nrows + 1) * 4);
+  if (nnz > 0) {
+    rc |= b200_h2d(M->d_colidx, h_colidx, (size_t)nnz * 4);
+    rc |= b200_h2d(M->d_vals, h_vals, (size_t)nnz * 8);
+  }
+  if (M->ntiles > 0) rc |= b200_h2d(M->d_tiles, tiles.data(), (size_t)M->ntiles * sizeof(int4));
+  rc |= b200_h2d(M->d_cta_tile_begin, begin.data(), (size_t)(grid + 1) * 4);
+  rc |= b200_sync();  // host vectors go out of scope
+  if (rc != 0) {
+    b200_spmv_destroy(M);
+    return nullptr;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(spmv_csr_stream_kernel<B200_POST_NONE>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spmv_smem_bytes());
+    cudaFuncSetAttribute(spmv_csr_stream_kernel<B200_POST_DIV>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spmv_smem_bytes());
+    cudaFuncSetAttribute(spmv_csr_stream_kernel<B200_POST_FMA_DOT>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spmv_smem_bytes());
+    cudaFuncSetAttribute(spmv_csr_stream_kernel<B200_POST_FMA>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spmv_smem_bytes());
+    attr_done = true;
+  }
+  return M;
+}
+
+extern "C" void b200_spmv_destroy(B200Spmv *M) {
+  if (!M) return;
+  b200_free(M->d_rowptr);
+  b200_free(M->d_colidx);
+  b200_free(M->d_vals);
+  b200_free(M->d_tiles);
+  b200_free(M->d_cta_tile_begin);
+  b200_free(M->d_partials);
+  b200_free(M->d_counter);
+  free(M);
+}
+
+extern "C" int b200_spmv_nrows(const B200Spmv *M) { return M->nrows; }
+extern "C" int b200_spmv_ncols(const B200Spmv *M) { return M->ncols; }
+extern "C" long long b200_spmv_nnz(const B200Spmv *M) { return M->nnz; }
+extern "C" const double *b200_spmv_vals(const B200Spmv *M) { return M->d_vals; }
+extern "C" const int *b200_spmv_colidx(const B200Spmv *M) { return M->d_colidx; }
+extern "C" const int *b200_spmv_rowptr(const B200Spmv *M) { return M->d_rowptr; }
+extern "C" double b200_spmv_alg_bytes(const B200Spmv *M, int extra_row_vectors) {
+  return 12.0 * (double)M->nnz + 4.0 * (M->nrows + 1.0) + 8.0 * M->ncols +
+         8.0 * M->nrows * (1.0 + extra_row_vectors);
+}
+
+extern "C" int b200_spmv(const B200Spmv *M, const B200SpmvArgs *a) {
+  if (M->nrows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)b200_stream();
+  const size_t smem = spmv_smem_bytes();
+  dim3 grid(M->grid), block(SPMV_THREADS);
+#define LAUNCH(POSTV)                                                                          \
+  spmv_csr_stream_kernel<POSTV><<<grid, block, smem, st>>>(                                    \
+      M->d_rowptr, M->d_colidx, M->d_vals, M->d_tiles, M->d_cta_tile_begin, a->d_x, a->d_y,    \
+      a->d_init, a->init_sign, a->d_d, a->d_v, a->d_dot, a->hook, a->d_hook_arg, a->d_skip,    \
+      M->d_partials, M->d_counter)
+  switch (a->post) {
+    case B200_POST_NONE: LAUNCH(B200_POST_NONE); break;
+    case B200_POST_DIV: LAUNCH(B200_POST_DIV); break;
+    case B200_POST_FMA_DOT: LAUNCH(B200_POST_FMA_DOT); break;
+    case B200_POST_FMA: LAUNCH(B200_POST_FMA); break;
+    default: return -1;
+  }
+#undef LAUNCH
+  b200_count_launch(1);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}

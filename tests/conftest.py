@@ -1,0 +1,32 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+REF_LIB = os.path.join(REF_DIR, "libscsindir_ref.so")
+REF_LIB_NOLAPACK = os.path.join(REF_DIR, "libscsindir_ref_nolapack.so")
+ORACLE_LIB = os.path.join(ROOT, "oracle", "liboracle.so")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def lib():
+    from scs_b200 import capi
+    return capi.load()
+
+
+@pytest.fixture(scope="session")
+def reflib():
+    """The UNMODIFIED reference CPU-indirect build (oracle/_ref). Checker only."""
+    from scs_b200 import capi
+    if not os.path.exists(REF_LIB):
+        pytest.skip("oracle/_ref not built (run `make -C oracle ref` where /root/reference exists)")
+    return capi.load_reference(REF_LIB)

@@ -14,12 +14,13 @@
 //     L2 evict_first) of the tile's value and column-index slices into shared
 //     memory, completion signalled on an mbarrier;
 //   * phase 1: all threads gather x[col] for the tile's entries (coalesced reads
-//     of idx from smem, up to 4 independent 8-byte gathers per thread in flight);
-//   * phase 2: L lanes per row (L=1 for short rows) run the FMA chain over the
-//     row's (val, x) pairs from shared memory IN STORAGE ORDER -- for L=1 this is
-//     the same sequential fma chain the reference's scalar loop performs, so the
-//     result is bit-identical to the CPU; L>1 finishes with a fixed xor-shuffle
-//     tree;
+//     of idx from smem, up to 4 independent 8-byte gathers per thread in flight)
+//     and store the rounded products val*x[col] in shared memory;
+//   * phase 2: L lanes per row (L=1 for short rows) add the row's products IN
+//     STORAGE ORDER -- for L=1 this is the same sequential multiply-then-add chain
+//     as the reference's scalar loop `yj += Ax[p] * x[Ai[p]]` (which gcc does not
+//     contract to fma in the oracle build, checked with objdump), so the result
+//     is bit-identical to the CPU; L>1 finishes with a fixed xor-shuffle tree;
 //   * fused epilogues: y = s | s / d[r] | fma(d[r], v[r], s) plus the dot
 //     product v'y with a deterministic last-block reduction and an optional
 //     hook that turns the dot into the CG step length on the device.
@@ -154,7 +155,7 @@ spmv_csr_stream_kernel(const int *__restrict__ rowptr, const int *__restrict__ c
     {
       int k = tid;
 #pragma unroll 4
-      for (; k < nnz; k += SPMV_THREADS) s_xg[k] = __ldg(&x[ti[k]]);
+      for (; k < nnz; k += SPMV_THREADS) s_xg[k] = __dmul_rn(tv[k], __ldg(&x[ti[k]]));
     }
     __syncthreads();
 
@@ -165,7 +166,7 @@ spmv_csr_stream_kernel(const int *__restrict__ rowptr, const int *__restrict__ c
           const int row = row0 + r;
           const int a = __ldg(&rowptr[row]) - k0, b = __ldg(&rowptr[row + 1]) - k0;
           double s = (init != nullptr) ? init_sign * init[row] : 0.0;
-          for (int k = a; k < b; ++k) s = fma(tv[k], s_xg[k], s);
+          for (int k = a; k < b; ++k) s = __dadd_rn(s, s_xg[k]);
           spmv_epilogue<POST>(s, row, y, d, v, dot_acc);
         }
       } else {
@@ -182,7 +183,7 @@ spmv_csr_stream_kernel(const int *__restrict__ rowptr, const int *__restrict__ c
             b = __ldg(&rowptr[row + 1]) - k0;
           }
           double s = 0.0;
-          for (int k = a + lig; k < b; k += L) s = fma(tv[k], s_xg[k], s);
+          for (int k = a + lig; k < b; k += L) s = __dadd_rn(s, s_xg[k]);
           for (int o = L >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
           if (valid && lig == 0) {
             if (init != nullptr) s += init_sign * init[row];
@@ -193,7 +194,7 @@ spmv_csr_stream_kernel(const int *__restrict__ rowptr, const int *__restrict__ c
     } else {
       // chunk of one long row: whole block reduces, thread 0 carries across chunks
       double part[1] = {0.0};
-      for (int k = tid; k < nnz; k += SPMV_THREADS) part[0] = fma(tv[k], s_xg[k], part[0]);
+      for (int k = tid; k < nnz; k += SPMV_THREADS) part[0] = __dadd_rn(part[0], s_xg[k]);
       block_sum<1>(part, s_red);
       if (tid == 0) {
         if (type == TILE_LONG_FIRST || type == TILE_LONG_ONLY)

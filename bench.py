@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- ADMM iterations/sec of the SCS hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2] [--scale f]
+
+A "step" is ONE ADMM iteration (normalise v -> indirect KKT solve by device PCG ->
+cone projection -> dual update, with Anderson acceleration every 10th step and the
+residual / scale check every 25th) on the synthetic workload named by `--config`
+(default C2: random sparse SOCP n=1e6, m=3e6, nnz=1e7, 50 SOC cones, fp64), run
+through the public C ABI (scs_init / scs_solve) of scs_b200/libscs_b200.so.
+
+  value  : K / (device-resident timed solve), problem already resident in HBM
+           (a warm-up solve of W iterations ran before; eps = 0 so exactly K
+           iterations execute).  CUDA events bracket the timed region; the
+           wall clock of the same region is printed too (they agree: the solve
+           synchronises at its end).
+  e2e    : K / wall time of the whole host-buffer call scs() = scs_init (H2D of A,
+           b, c; host equilibration) + scs_solve(K) + D2H of (x, y, s) + scs_finish.
+  roofline: the SpMV kernels (dominant: ~78 % of the algorithmic bytes of a CG
+           iteration), timed live with CUDA events, alternating A x and A'y so
+           that the 2 x 124 MB of matrix data never sit in the 126 MB L2.
+  cpu_baseline: the UNMODIFIED reference CPU-indirect solver (oracle/_ref, all host
+           threads via its OpenMP build) on a bounded sample of the same workload.
+
+--impl reference times that same reference solver as the whole arm.
+N > 1: one process per GPU; each rank solves an independent instance of the same
+workload (weak scaling, no data-path collective); value = sum over ranks / max time.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIG_DESC = {
+    "C1": "random sparse SOCP n=1e3 m=4e3 nnz=3.2e4 (reference demo size)",
+    "C2": "random sparse SOCP n=1e6 m=3e6 nnz=1e7, 50 SOC cones, fp64",
+    "C3": "random sparse LP (box+pos cone) n=5e6 m=5e6 nnz=5e7",
+    "C4": "SDP 200 PSD(100) + 1e5 linear rows, n=1e5, nnz=2e7",
+    "C5": "mixed SOCP+SDP n=2e6 m=6e6 nnz=3e7, AA mem 10",
+}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.stop_flag = threading.Event()
+        self.rows = []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
+                                  "--format=csv,noheader,nounits", "-lms", "100"],
+                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        while not self.stop_flag.is_set():
+            line = p.stdout.readline()
+            if not line:
+                break
+            self.rows.append([t.strip() for t in line.split(",")])
+        p.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+        except Exception:
+            pass
+    return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s"
+
+
+def build_problem(name, scale, seed):
+    from scs_b200 import problems
+    t0 = time.time()
+    prob = problems.config(name, scale=scale, seed=seed)
+    return prob, time.time() - t0
+
+
+def run_solver(lib, capi, hp, settings_over, w=None, warm=False, sol_arrays=None):
+    """scs_init (if w is None) + scs_solve; returns (w, info, sol arrays)."""
+    st = capi.default_settings(lib, verbose=0, **settings_over)
+    if w is None:
+        w = lib.scs_init(C.byref(hp.data), C.byref(hp.cone), C.byref(st))
+        if not w:
+            raise RuntimeError("scs_init failed")
+    if sol_arrays is None:
+        sol_arrays = (np.zeros(hp.n), np.zeros(hp.m), np.zeros(hp.m))
+    sol = capi.ScsSolution(*(capi.dptr(a) for a in sol_arrays))
+    info = capi.ScsInfo()
+    lib.scs_solve(w, C.byref(sol), C.byref(info), 1 if warm else 0)
+    return w, info, sol_arrays
+
+
+def ref_lib_path(omp=True):
+    d = os.path.join(ROOT, "oracle", "_ref")
+    p = os.path.join(d, "libscsindir_ref_omp.so" if omp else "libscsindir_ref.so")
+    return p if os.path.exists(p) else None
+
+
+def time_reference(capi, prob, iters, omp=True):
+    """K ADMM iterations of the UNMODIFIED reference CPU-indirect solver; returns dict."""
+    path = ref_lib_path(omp)
+    if path is None:
+        return None
+    ncores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(ncores))
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", str(ncores))
+    ref = capi.load_reference(path)
+    hp = capi.HostProblem(prob["A"], prob["b"], prob["c"], prob["cone"])
+    st = capi.default_settings(ref, verbose=0, max_iters=int(iters), eps_abs=0.0, eps_rel=0.0, eps_infeas=0.0)
+    x, y, s = np.zeros(hp.n), np.zeros(hp.m), np.zeros(hp.m)
+    sol = capi.ScsSolution(capi.dptr(x), capi.dptr(y), capi.dptr(s))
+    info = capi.ScsInfo()
+    t0 = time.time()
+    w = ref.scs_init(C.byref(hp.data), C.byref(hp.cone), C.byref(st))
+    t_init = time.time() - t0
+    t0 = time.time()
+    ref.scs_solve(w, C.byref(sol), C.byref(info), 0)
+    t_solve = time.time() - t0
+    ref.scs_finish(w)
+    return {"iters": int(info.iter), "solve_s": t_solve, "init_s": t_init,
+            "its_per_s": info.iter / t_solve, "e2e_its_per_s": info.iter / (t_solve + t_init),
+            "cores": ncores, "lin_sys_ms": info.lin_sys_time, "cone_ms": info.cone_time,
+            "accel_ms": info.accel_time, "lib": os.path.basename(path)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=os.environ.get("SCS_BENCH_CONFIG", "C2"))
+    ap.add_argument("--scale", type=float, default=float(os.environ.get("SCS_BENCH_SCALE", "1.0")))
+    ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from scs_b200 import capi
+
+    base = {"metric": "ADMM iters/sec", "unit": "iters/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic"}
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        prob, gen_s = build_problem(args.config, args.scale, args.seed)
+        # bounded: at most ~150 s of CPU work -> estimate from a short probe
+        probe = time_reference(capi, prob, max(3, min(args.warmup, 5)))
+        if probe is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}))
+            return 0
+        budget_s = float(os.environ.get("SCS_BENCH_REF_BUDGET_S", "150"))
+        k = int(max(5, min(args.steps, budget_s * probe["its_per_s"])))
+        r = time_reference(capi, prob, k)
+        out = dict(base)
+        out.update({
+            "impl": "reference", "value": r["its_per_s"], "ms_per_step": 1e3 / r["its_per_s"], "n_gpus": world,
+            "steps_run": r["iters"],
+            "config": {"workload": f"{args.config}: {CONFIG_DESC.get(args.config, '')}", "scale": args.scale,
+                       "n": prob["n"], "m": prob["m"], "nnz": prob["nnz"], "settings": "SCS defaults, eps=0"},
+            "cpu_baseline": {"value": r["its_per_s"], "unit": "iters/s", "cores": r["cores"], "kind": "reference",
+                             "sample": f"{r['iters']} ADMM iterations of the unmodified reference CPU-indirect "
+                                       f"solver ({r['lib']}, OMP_NUM_THREADS={r['cores']}) on the full workload"},
+            "e2e": {"value": r["e2e_its_per_s"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        })
+        print(json.dumps(out))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    os.environ["SCS_B200_DEVICE"] = str(local_rank)
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = capi.load()
+    if not lib.scs_b200_device_ok():
+        raise RuntimeError("scs_b200: no usable sm_100 device (there is no CPU fallback)")
+
+    prob, gen_s = build_problem(args.config, args.scale, args.seed + rank)
+    hp = capi.HostProblem(prob["A"], prob["b"], prob["c"], prob["cone"])
+    n, m, nnz = prob["n"], prob["m"], prob["nnz"]
+    eps0 = dict(eps_abs=0.0, eps_rel=0.0, eps_infeas=0.0)
+
+    # ---- e2e: whole host-buffer call (init + K iterations + finish), copies inside the timed region
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    barrier()
+    t0 = time.time()
+    w, info_e, sols = run_solver(lib, capi, hp, dict(max_iters=args.steps, **eps0))
+    lib.scs_finish(w)
+    torch.cuda.synchronize()
+    e2e_s = time.time() - t0
+    h2d = nnz * 12 + (n + 1) * 4 + (m + n) * 8          # A (vals+idx+ptr), b, c
+    d2h = (n + 2 * m) * 8                                # x, y, s
+
+    # ---- device-resident: init once, W warm-up steps, then exactly K timed steps (warm-started)
+    st = capi.default_settings(lib, verbose=0, max_iters=args.warmup, **eps0)
+    w = lib.scs_init(C.byref(hp.data), C.byref(hp.cone), C.byref(st))
+    if not w:
+        raise RuntimeError("scs_init failed")
+    sol = capi.ScsSolution(*(capi.dptr(a) for a in sols))
+    info = capi.ScsInfo()
+    lib.scs_solve(w, C.byref(sol), C.byref(info), 0)          # W untimed steps
+    assert lib.scs_b200_set_max_iters(w, args.steps) == 0
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = lib.scs_b200_launch_count()
+    t0 = time.time()
+    ev0.record()
+    lib.scs_solve(w, C.byref(sol), C.byref(info), 1)
+    ev1.record()
+    barrier()
+    wall_s = time.time() - t0
+    launches = lib.scs_b200_launch_count() - launches0
+    sampler.stop_flag.set()
+    stats = capi.ScsB200Stats()
+    lib.scs_b200_get_stats(w, C.byref(stats))
+    solve_s = info.solve_time / 1e3
+    iters = int(info.iter)
+    lib.scs_finish(w)
+
+    # max over ranks / sum of work
+    tmax = solve_s
+    total_iters = iters
+    if world > 1:
+        t = torch.tensor([solve_s, float(iters), e2e_s], device="cuda", dtype=torch.float64)
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone()
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        tmax, total_iters, e2e_s = float(tm[0]), int(ts[1]), float(tm[2])
+    value = total_iters / tmax
+    e2e_value = (args.steps * world) / e2e_s
+
+    # ---- roofline of the dominant kernels, timed live with CUDA events (rank 0)
+    roof = None
+    extra = {}
+    cpu_base = None
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        dr = np.empty(n + m + 1)
+        z = int(prob["cone"].get("z", 0))
+        dr[:n] = 1e-6
+        dr[n:n + z] = 1.0 / 100.0
+        dr[n + z:n + m] = 10.0
+        dr[n + m] = 10.0
+        lw = lib.scs_init_lin_sys_work(C.byref(hp.A), None, capi.dptr(dr))
+        ab = C.c_double(0.0)
+        rows = []
+        for op, name in ((0, "spmv_csr_stream<POST_NONE> y=A x (rows of A, 3.3 nnz/row)"),
+                         (1, "spmv_csr_stream<POST_NONE> y=A'x (cols of A, 10 nnz/row)")):
+            ms = lib.scs_b200_time_spmv(lw, op, 20, C.byref(ab))
+            rows.append({"kernel": name, "ms": ms, "alg_bytes": ab.value, "achieved": ab.value / ms / 1e6,
+                         "frac": ab.value / ms / 1e6 / peak})
+        ms_cg = lib.scs_b200_time_cg_iter(lw, 50, C.byref(ab))
+        cg_row = {"kernel": "one CG iteration (K1 A p, K2 A' z + dot, K3 update, K4 p)", "ms": ms_cg,
+                  "alg_bytes": ab.value, "achieved": ab.value / ms_cg / 1e6, "frac": ab.value / ms_cg / 1e6 / peak}
+        lib.scs_free_lin_sys_work(lw)
+        dom = max(rows, key=lambda r: r["ms"])
+        roof = {"bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                "traffic": None, "kernel": dom["kernel"], "ms_per_launch": dom["ms"],
+                "alg_bytes_per_launch": dom["alg_bytes"], "peak_source": peak_src,
+                "l2_flush": "alternating A / A' launches: 2 x matrix bytes > L2"}
+        extra["roofline_all"] = rows + [cg_row]
+        if not args.no_cpu_baseline:
+            try:
+                k = 8 if args.scale >= 0.5 else 40
+                r = time_reference(capi, prob, k)
+                if r:
+                    cpu_base = {"value": r["its_per_s"], "unit": "iters/s", "cores": r["cores"], "kind": "reference",
+                                "sample": f"{r['iters']} ADMM iterations of the unmodified reference CPU-indirect "
+                                          f"solver ({r['lib']}) on the same workload (setup {r['init_s']:.1f}s excluded)"}
+            except Exception as e:  # the checker must never break the measurement
+                cpu_base = {"value": None, "unit": "iters/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+
+    if rank == 0:
+        out = dict(base)
+        out.update({
+            "value": value, "ms_per_step": 1e3 * tmax / max(iters, 1),
+            "config": {"workload": f"{args.config}: {CONFIG_DESC.get(args.config, '')}", "scale": args.scale,
+                       "n": n, "m": m, "nnz": nnz, "settings": "SCS defaults (AA mem 10, adaptive scale), eps=0 so "
+                       "exactly K iterations run", "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas",
+                       "l2": "working set (A, A' = 2 x 124 MB + vectors) exceeds the 126 MB L2"},
+            "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": h2d / args.steps,
+                    "d2h_bytes_per_step": d2h / args.steps,
+                    "note": "whole scs() on host buffers: scs_init (H2D + host equilibration) + K iterations + D2H"},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "cg_iters_per_step": stats.cg_iters / max(iters, 1),
+            "timed_wall_s": wall_s, "timed_device_event_s": ev0.elapsed_time(ev1) / 1e3,
+            "lin_sys_ms": info.lin_sys_time, "cone_ms": info.cone_time, "accel_ms": info.accel_time,
+            "setup_ms": info.setup_time, "problem_gen_s": gen_s,
+        })
+        if roof:
+            out["roofline"] = roof
+        if cpu_base:
+            out["cpu_baseline"] = cpu_base
+        out.update(extra)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

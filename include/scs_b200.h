@@ -209,10 +209,11 @@ scs_int scs_b200_accum_by_a(ScsLinSysWork *w, const scs_float *x, scs_float *y,
 scs_int scs_b200_accum_by_atrans(ScsLinSysWork *w, const scs_float *x,
                                  scs_float *y, scs_int accumulate);
 
-/* Time `reps` back-to-back launches of one device SpMV (op 0: A x via the
- * row-major copy, op 1: A' x via the CSC arrays) with CUDA events; inputs
- * resident in HBM.  Returns average milliseconds per launch, <0 on error.
- * *alg_bytes receives the algorithmic bytes of one launch. */
+/* Time one device SpMV (op 0: A x via the row-major copy, op 1: A' x via the
+ * CSC arrays) with per-launch CUDA events over `reps` launches; A x and A'x are
+ * launched alternately so neither matrix stays in L2 (as in the CG loop).
+ * Inputs resident in HBM.  Returns average milliseconds per launch, <0 on
+ * error.  *alg_bytes receives the algorithmic bytes of one launch. */
 double scs_b200_time_spmv(ScsLinSysWork *w, scs_int op, scs_int reps,
                           double *alg_bytes);
 /* Time `reps` CG iterations (4 kernels each) the same way. */
@@ -255,6 +256,9 @@ typedef struct {
   scs_int n_gpus;
 } ScsB200Stats;
 scs_int scs_b200_get_stats(const ScsWork *w, ScsB200Stats *out);
+/* Change max_iters of a live workspace (the settings are deep-copied at
+ * scs_init; used by bench.py to run W warm-up and then exactly K timed steps). */
+scs_int scs_b200_set_max_iters(ScsWork *w, scs_int max_iters);
 
 /* Number of kernels this library has launched in this process. */
 long long scs_b200_launch_count(void);

@@ -239,6 +239,8 @@ def _declare(lib, ours):
     lib.scs_b200_aa_get_stats.argtypes = [C.c_void_p]
     lib.scs_b200_get_stats.restype = C.c_int
     lib.scs_b200_get_stats.argtypes = [C.c_void_p, C.POINTER(ScsB200Stats)]
+    lib.scs_b200_set_max_iters.restype = C.c_int
+    lib.scs_b200_set_max_iters.argtypes = [C.c_void_p, C.c_int]
     lib.scs_b200_launch_count.restype = C.c_longlong
     lib.scs_b200_device_ok.restype = C.c_int
 
@@ -254,7 +256,8 @@ def load():
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(make -C scs_b200/csrc). There is no CPU fallback.")
-        lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        # RTLD_LOCAL: our scs_* symbols must not interpose on the reference build loaded by the tests
+        lib = C.CDLL(LIB_PATH, mode=C.RTLD_LOCAL)
         _declare(lib, ours=True)
         _lib = lib
     return _lib

@@ -69,6 +69,8 @@ typedef struct {
 } B200SpmvArgs;
 
 int b200_spmv(const B200Spmv *M, const B200SpmvArgs *a);
+/* per-launch CUDA-event timing of M0 and M1 launched alternately (cold L2), ms per launch */
+int b200_spmv_time_pair(const B200Spmv *M0, const B200Spmv *M1, int reps, double *out_ms);
 
 /* ------------------------------------------------------------ CG --------- */
 /* Device-resident control block of one PCG solve (reference

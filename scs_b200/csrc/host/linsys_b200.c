@@ -267,29 +267,10 @@ scs_int scs_b200_accum_by_atrans(ScsLinSysWork *w, const scs_float *x, scs_float
 
 /* --- device timing helpers for bench.py (inputs resident in HBM) --------- */
 double scs_b200_time_spmv(ScsLinSysWork *w, scs_int op, scs_int reps, double *alg_bytes) {
-  const B200Spmv *M = op == 0 ? w->A : w->At;
-  const int ncols = b200_spmv_ncols(M), nrows = b200_spmv_nrows(M);
-  B200SpmvArgs a;
-  double ms = -1.0;
-  int i;
-  double *d_x = (double *)b200_malloc((size_t)ncols * 8);
-  double *d_y = (double *)b200_malloc((size_t)nrows * 8);
-  double *hx = (double *)malloc((size_t)ncols * 8);
-  if (!d_x || !d_y || !hx) goto out;
-  for (i = 0; i < ncols; ++i) hx[i] = 1.0 + 1e-3 * (double)(i % 1000);
-  if (b200_h2d(d_x, hx, (size_t)ncols * 8) != 0) goto out;
-  memset(&a, 0, sizeof(a));
-  a.d_x = d_x; a.d_y = d_y; a.init_sign = 1.0; a.post = B200_POST_NONE;
-  for (i = 0; i < 3; ++i) if (b200_spmv(M, &a) != 0) goto out;
-  if (b200_sync() != 0) goto out;
-  if (b200_timer_start() != 0) goto out;
-  for (i = 0; i < reps; ++i) if (b200_spmv(M, &a) != 0) goto out;
-  ms = b200_timer_stop_ms();
-  if (ms >= 0) ms /= (double)reps;
-  if (alg_bytes) *alg_bytes = b200_spmv_alg_bytes(M, 0);
-out:
-  b200_free(d_x); b200_free(d_y); free(hx);
-  return ms;
+  double ms[2] = {-1.0, -1.0};
+  if (b200_spmv_time_pair(w->A, w->At, reps, ms) != 0) return -1.0;
+  if (alg_bytes) *alg_bytes = b200_spmv_alg_bytes(op == 0 ? w->A : w->At, 0);
+  return ms[op == 0 ? 0 : 1];
 }
 
 double scs_b200_time_cg_iter(ScsLinSysWork *w, scs_int reps, double *alg_bytes) {

@@ -931,5 +931,10 @@ scs_int scs_b200_get_stats(const ScsWork *w, ScsB200Stats *out) {
   out->n_gpus = 1;
   return 0;
 }
+scs_int scs_b200_set_max_iters(ScsWork *w, scs_int max_iters) {
+  if (!w || max_iters <= 0) return -1;
+  w->stgs->max_iters = max_iters;
+  return 0;
+}
 long long scs_b200_launch_count(void) { return b200_launches(); }
 scs_int scs_b200_device_ok(void) { return b200_device_ok(); }

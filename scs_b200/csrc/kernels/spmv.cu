@@ -412,3 +412,57 @@ extern "C" int b200_spmv(const B200Spmv *M, const B200SpmvArgs *a) {
   CUDA_OK(cudaGetLastError());
   return 0;
 }
+
+// Alternating launches of two operators (A then A'), every launch bracketed by its own CUDA
+// events on the library stream: the other operator's matrix stream evicts this one's from L2,
+// as in the CG loop. out_ms[0], out_ms[1] = average duration per launch of M0, M1.
+extern "C" int b200_spmv_time_pair(const B200Spmv *M0, const B200Spmv *M1, int reps, double *out_ms) {
+  cudaStream_t st = (cudaStream_t)b200_stream();
+  const B200Spmv *Ms[2] = {M0, M1};
+  double *d_x[2] = {nullptr, nullptr}, *d_y[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> ev((size_t)reps * 4);
+  int rc = -1;
+  for (auto &e : ev) e = nullptr;
+  for (int k = 0; k < 2; ++k) {
+    d_x[k] = (double *)b200_malloc((size_t)Ms[k]->ncols * 8);
+    d_y[k] = (double *)b200_malloc((size_t)Ms[k]->nrows * 8);
+    if (!d_x[k] || !d_y[k]) goto out;
+    std::vector<double> hx((size_t)Ms[k]->ncols);
+    for (size_t i = 0; i < hx.size(); ++i) hx[i] = 1.0 + 1e-3 * (double)(i % 1000);
+    if (b200_h2d(d_x[k], hx.data(), hx.size() * 8) != 0) goto out;
+  }
+  for (auto &e : ev)
+    if (cudaEventCreate(&e) != cudaSuccess) goto out;
+  {
+    B200SpmvArgs a[2];
+    for (int k = 0; k < 2; ++k) {
+      memset(&a[k], 0, sizeof(B200SpmvArgs));
+      a[k].d_x = d_x[k]; a[k].d_y = d_y[k]; a[k].init_sign = 1.0; a[k].post = B200_POST_NONE;
+    }
+    for (int w = 0; w < 3; ++w)
+      for (int k = 0; k < 2; ++k)
+        if (b200_spmv(Ms[k], &a[k]) != 0) goto out;
+    if (cudaStreamSynchronize(st) != cudaSuccess) goto out;
+    for (int r = 0; r < reps; ++r)
+      for (int k = 0; k < 2; ++k) {
+        cudaEventRecord(ev[(size_t)r * 4 + 2 * k], st);
+        if (b200_spmv(Ms[k], &a[k]) != 0) goto out;
+        cudaEventRecord(ev[(size_t)r * 4 + 2 * k + 1], st);
+      }
+    if (cudaStreamSynchronize(st) != cudaSuccess) goto out;
+    out_ms[0] = out_ms[1] = 0.0;
+    for (int r = 0; r < reps; ++r)
+      for (int k = 0; k < 2; ++k) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[(size_t)r * 4 + 2 * k], ev[(size_t)r * 4 + 2 * k + 1]);
+        out_ms[k] += ms;
+      }
+    out_ms[0] /= reps;
+    out_ms[1] /= reps;
+    rc = 0;
+  }
+out:
+  for (auto &e : ev) if (e) cudaEventDestroy(e);
+  for (int k = 0; k < 2; ++k) { b200_free(d_x[k]); b200_free(d_y[k]); }
+  return rc;
+}

@@ -130,6 +130,16 @@ k_cg_init(int n, int warm, double *__restrict__ x /* b[0:n] */, const double *__
 
 // ---------------------------------------------------------------------------
 // K3 (private.c:181-211): x += alpha p; r -= alpha Gp; z = M r; reductions.
+// 128-bit loads/stores (double2), 2 independent double2 per thread per trip.
+__device__ __forceinline__ void cg_update_elem(double alpha, double nalpha, double &x, double &r,
+                                               double p, double gp, double m, double &z,
+                                               double &acc0, double &acc1) {
+  x = fma(alpha, p, x);
+  r = fma(nalpha, gp, r);
+  z = r * m;
+  acc0 = fma(z, r, acc0);
+  acc1 = fmax(acc1, fabs(r));
+}
 __global__ void __launch_bounds__(VEC_THREADS)
 k_cg_update(int n, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
             const double *__restrict__ Gp, const double *__restrict__ M, double *__restrict__ z,
@@ -139,14 +149,35 @@ k_cg_update(int n, double *__restrict__ x, double *__restrict__ r, const double 
   const double alpha = ctl->alpha;
   const double nalpha = -alpha;
   double acc0 = 0.0, acc1 = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    x[i] = fma(alpha, p[i], x[i]);
-    const double ri = fma(nalpha, Gp[i], r[i]);
-    r[i] = ri;
-    const double zi = ri * M[i];
-    z[i] = zi;
-    acc0 = fma(zi, ri, acc0);
-    acc1 = fmax(acc1, fabs(ri));
+  const int n2 = n >> 1;
+  double2 *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r),
+          *z2 = reinterpret_cast<double2 *>(z);
+  const double2 *p2 = reinterpret_cast<const double2 *>(p), *g2 = reinterpret_cast<const double2 *>(Gp),
+                *m2 = reinterpret_cast<const double2 *>(M);
+  const int stride = gridDim.x * blockDim.x;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < n2; i += 2 * stride) {
+    double2 xa = x2[i], ra = r2[i], pa = p2[i], ga = g2[i], ma = m2[i], za;
+    double2 xb = x2[i + stride], rb = r2[i + stride], pb = p2[i + stride], gb = g2[i + stride],
+            mb = m2[i + stride], zb;
+    cg_update_elem(alpha, nalpha, xa.x, ra.x, pa.x, ga.x, ma.x, za.x, acc0, acc1);
+    cg_update_elem(alpha, nalpha, xa.y, ra.y, pa.y, ga.y, ma.y, za.y, acc0, acc1);
+    cg_update_elem(alpha, nalpha, xb.x, rb.x, pb.x, gb.x, mb.x, zb.x, acc0, acc1);
+    cg_update_elem(alpha, nalpha, xb.y, rb.y, pb.y, gb.y, mb.y, zb.y, acc0, acc1);
+    x2[i] = xa; r2[i] = ra; z2[i] = za;
+    x2[i + stride] = xb; r2[i + stride] = rb; z2[i + stride] = zb;
+  }
+  for (; i < n2; i += stride) {
+    double2 xa = x2[i], ra = r2[i], pa = p2[i], ga = g2[i], ma = m2[i], za;
+    cg_update_elem(alpha, nalpha, xa.x, ra.x, pa.x, ga.x, ma.x, za.x, acc0, acc1);
+    cg_update_elem(alpha, nalpha, xa.y, ra.y, pa.y, ga.y, ma.y, za.y, acc0, acc1);
+    x2[i] = xa; r2[i] = ra; z2[i] = za;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int k = n - 1;
+    double xv = x[k], rv = r[k], zv;
+    cg_update_elem(alpha, nalpha, xv, rv, p[k], Gp[k], M[k], zv, acc0, acc1);
+    x[k] = xv; r[k] = rv; z[k] = zv;
   }
   double sm[1] = {acc0}, mx[1] = {acc1};
   block_sum<1>(sm, s_red);
@@ -176,8 +207,23 @@ __global__ void __launch_bounds__(VEC_THREADS)
 k_cg_pupdate(int n, double *__restrict__ p, const double *__restrict__ z, const B200CgCtl *ctl) {
   if (ctl->done) return;
   const double beta = ctl->beta;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    p[i] = fma(beta, p[i], z[i]);
+  const int n2 = n >> 1;
+  double2 *p2 = reinterpret_cast<double2 *>(p);
+  const double2 *z2 = reinterpret_cast<const double2 *>(z);
+  const int stride = gridDim.x * blockDim.x;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < n2; i += 2 * stride) {
+    double2 pa = p2[i], za = z2[i], pb = p2[i + stride], zb = z2[i + stride];
+    pa.x = fma(beta, pa.x, za.x); pa.y = fma(beta, pa.y, za.y);
+    pb.x = fma(beta, pb.x, zb.x); pb.y = fma(beta, pb.y, zb.y);
+    p2[i] = pa; p2[i + stride] = pb;
+  }
+  for (; i < n2; i += stride) {
+    double2 pa = p2[i], za = z2[i];
+    pa.x = fma(beta, pa.x, za.x); pa.y = fma(beta, pa.y, za.y);
+    p2[i] = pa;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = fma(beta, p[n - 1], z[n - 1]);
 }
 
 __global__ void k_zero_if(long long len, double *__restrict__ v, const int *flag) {
@@ -227,7 +273,9 @@ static int mat_vec(B200Cg *cg, const double *d_x, double *d_y, int with_dot, con
 static int cg_iteration(B200Cg *cg, double *d_x) {
   cudaStream_t st = (cudaStream_t)b200_stream();
   const int n = cg->n;
-  const int g = vec_grid(n);
+  int g = (n + VEC_THREADS * 8 - 1) / (VEC_THREADS * 8);
+  if (g > 2 * b200_num_sms()) g = 2 * b200_num_sms();
+  if (g < 1) g = 1;
   if (mat_vec(cg, cg->d_p, cg->d_Gp, 1, &cg->d_ctl->done) != 0) return -1;
   k_cg_update<<<g, VEC_THREADS, 0, st>>>(n, d_x, cg->d_r, cg->d_p, cg->d_Gp, cg->d_M, cg->d_z,
                                          cg->d_ctl, cg->d_partials, cg->d_counter);

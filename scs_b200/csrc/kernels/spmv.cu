@@ -37,7 +37,8 @@
 #define SPMV_STAGES 3
 #define SPMV_TILE_NNZ 2048
 #define SPMV_TILE_CAP (SPMV_TILE_NNZ + 8)
-#define SPMV_TILE_ROWS 2048
+#define SPMV_TILE_ROWS 1024
+#define SPMV_GATHERS (SPMV_TILE_NNZ / SPMV_THREADS)  // independent gathers per thread in flight
 
 // tile descriptor: x=row0, y=nrows | (type<<28) | (lg_lanes<<24), z=k0, w=nnz
 #define TILE_NORMAL 0
@@ -63,7 +64,8 @@ struct B200Spmv {
 
 static size_t spmv_smem_bytes() {
   return (size_t)SPMV_STAGES * SPMV_TILE_CAP * 8 + (size_t)SPMV_TILE_NNZ * 8 +
-         (size_t)SPMV_STAGES * SPMV_TILE_CAP * 4 + SPMV_STAGES * 8 + 64 * 8;
+         (size_t)SPMV_STAGES * SPMV_TILE_CAP * 4 + SPMV_STAGES * 8 + 64 * 8 +
+         (size_t)(SPMV_TILE_ROWS + 8) * 4;
 }
 
 __device__ __forceinline__ void spmv_issue_tile(const int4 t, int stage, double *s_vals, int *s_idx,
@@ -114,6 +116,7 @@ spmv_csr_stream_kernel(const int *__restrict__ rowptr, const int *__restrict__ c
   int *s_idx = reinterpret_cast<int *>(s_xg + SPMV_TILE_NNZ);
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_idx + SPMV_STAGES * SPMV_TILE_CAP);
   double *s_red = reinterpret_cast<double *>(s_bar + SPMV_STAGES);
+  int *s_rp = reinterpret_cast<int *>(s_red + 64);  // row pointers of the current tile
 
   const int tid = threadIdx.x;
   const int t_begin = cta_tile_begin[blockIdx.x];
@@ -151,11 +154,40 @@ spmv_csr_stream_kernel(const int *__restrict__ rowptr, const int *__restrict__ c
 
     mbar_wait(&s_bar[st], par);
 
-    // ---- phase 1: gather x for every entry of the tile
+    // ---- phase 1: stage the tile's row pointers, then gather x for every entry. All of a
+    // thread's loads are issued before any is consumed (SPMV_GATHERS independent 8-byte gathers
+    // in flight per thread): the L1 wavefront rate, not the latency, should bound this phase.
     {
-      int k = tid;
-#pragma unroll 4
-      for (; k < nnz; k += SPMV_THREADS) s_xg[k] = __dmul_rn(tv[k], __ldg(&x[ti[k]]));
+      constexpr int RPL = SPMV_TILE_ROWS / SPMV_THREADS + 1;
+      int rpv[RPL];
+      int c[SPMV_GATHERS];
+      double xv[SPMV_GATHERS];
+      if (type == TILE_NORMAL) {
+#pragma unroll
+        for (int u = 0; u < RPL; ++u) {
+          const int r = tid + u * SPMV_THREADS;
+          rpv[u] = (r <= nrows) ? __ldg(&rowptr[row0 + r]) : 0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < SPMV_GATHERS; ++u) {
+        const int k = tid + u * SPMV_THREADS;
+        c[u] = (k < nnz) ? ti[k] : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < SPMV_GATHERS; ++u) xv[u] = (c[u] >= 0) ? __ldg(&x[c[u]]) : 0.0;
+      if (type == TILE_NORMAL) {
+#pragma unroll
+        for (int u = 0; u < RPL; ++u) {
+          const int r = tid + u * SPMV_THREADS;
+          if (r <= nrows) s_rp[r] = rpv[u] - k0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < SPMV_GATHERS; ++u) {
+        const int k = tid + u * SPMV_THREADS;
+        if (k < nnz) s_xg[k] = __dmul_rn(tv[k], xv[u]);
+      }
     }
     __syncthreads();
 
@@ -164,7 +196,7 @@ spmv_csr_stream_kernel(const int *__restrict__ rowptr, const int *__restrict__ c
       if (lg == 0) {
         for (int r = tid; r < nrows; r += SPMV_THREADS) {
           const int row = row0 + r;
-          const int a = __ldg(&rowptr[row]) - k0, b = __ldg(&rowptr[row + 1]) - k0;
+          const int a = s_rp[r], b = s_rp[r + 1];
           double s = (init != nullptr) ? init_sign * init[row] : 0.0;
           for (int k = a; k < b; ++k) s = __dadd_rn(s, s_xg[k]);
           spmv_epilogue<POST>(s, row, y, d, v, dot_acc);
@@ -179,8 +211,8 @@ spmv_csr_stream_kernel(const int *__restrict__ rowptr, const int *__restrict__ c
           const int row = row0 + (valid ? r : 0);
           int a = 0, b = 0;
           if (valid) {
-            a = __ldg(&rowptr[row]) - k0;
-            b = __ldg(&rowptr[row + 1]) - k0;
+            a = s_rp[r];
+            b = s_rp[r + 1];
           }
           double s = 0.0;
           for (int k = a + lig; k < b; k += L) s = __dadd_rn(s, s_xg[k]);

@@ -260,6 +260,17 @@ scs_int scs_b200_get_stats(const ScsWork *w, ScsB200Stats *out);
  * scs_init; used by bench.py to run W warm-up and then exactly K timed steps). */
 scs_int scs_b200_set_max_iters(ScsWork *w, scs_int max_iters);
 
+/* Multi-GPU (one process per GPU, row-sharded KKT solve). Rank 0 creates the
+ * 128-byte NCCL unique id, the launcher distributes it (bench.py: torch.distributed), every
+ * rank calls scs_b200_comm_init BEFORE scs_init / scs_init_lin_sys_work. Every rank passes
+ * the same (full) problem; each keeps only its row block of A on its GPU. */
+scs_int scs_b200_comm_unique_id(char *out128);
+scs_int scs_b200_comm_init(scs_int rank, scs_int nranks, const char *id128);
+scs_int scs_b200_comm_finalize(void);
+/* contiguous row blocks of A balanced by nonzeros: offsets[nranks+1] (host logic, no GPU needed) */
+scs_int scs_b200_row_partition(scs_int m, scs_int n, const scs_int *Ap, const scs_int *Ai,
+                               scs_int nranks, scs_int *offsets);
+
 /* Number of kernels this library has launched in this process. */
 long long scs_b200_launch_count(void);
 /* 1 if a CUDA device of compute capability 10.x is usable, else 0. */

@@ -1,0 +1,30 @@
+"""Lean driver for ncu: build the C2 matrix, create the linsys workspace, run a few SpMV / CG launches."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from scs_b200 import capi, problems
+
+cfg = os.environ.get("CFG", "C2")
+scale = float(os.environ.get("SCALE", "1.0"))
+rng = np.random.default_rng(1234)
+n = int(1_000_000 * scale)
+m = 3 * n
+A = problems.random_sparse_csc(m, n, 10, rng)
+hp = capi.HostProblem(A, np.zeros(m), np.zeros(n), {"l": m})
+lib = capi.load()
+dr = np.empty(n + m + 1)
+dr[:n] = 1e-6
+dr[n:] = 10.0
+w = lib.scs_init_lin_sys_work(C.byref(hp.A), None, capi.dptr(dr))
+ab = C.c_double()
+reps = int(os.environ.get("REPS", "5"))
+for op in (0, 1):
+    ms = lib.scs_b200_time_spmv(w, op, reps, C.byref(ab))
+    print(f"spmv op{op}: {ms*1e3:.1f} us  {ab.value/ms/1e6:.0f} GB/s")
+ms = lib.scs_b200_time_cg_iter(w, reps, C.byref(ab))
+print(f"cg iter: {ms*1e3:.1f} us  {ab.value/ms/1e6:.0f} GB/s")
+lib.scs_free_lin_sys_work(w)

@@ -98,6 +98,10 @@ typedef struct {
   double *d_partials;  /* reduction slots */
   unsigned int *d_counter;
   B200CgCtl *h_ctl;    /* pinned mirror */
+  /* row-sharded mode (nranks > 1): A, At hold only rows [row0, row0+mloc) of the matrix */
+  int nranks, row0, mloc;
+  const int *offsets;  /* host: row block boundaries, nranks+1 */
+  double *d_red;       /* n: partial A_g' z before the all-reduce */
 } B200Cg;
 
 /* M_j = 1 / (R_x,j + P_jj + sum_k A_kj^2 / R_y,k)   (private.c:50-82) */
@@ -110,6 +114,12 @@ int b200_cg_solve(B200Cg *cg, double *d_b, const double *d_s, double tol, int ma
 /* one CG iteration (4 kernels), for timing */
 int b200_cg_one_iteration(B200Cg *cg, double *d_x);
 double b200_cg_iter_alg_bytes(const B200Cg *cg);
+
+/* ------------------------------------------------------------ comm (kernels/comm.cu) */
+int b200_comm_rank(void);
+int b200_comm_nranks(void);
+int b200_allreduce_sum(double *d_buf, size_t count);
+int b200_allgatherv(double *d_buf, const int *offsets);
 
 /* ------------------------------------------------------------ vector ops - */
 /* out = |a|_inf etc. are produced into device scalars; see admm.cu */

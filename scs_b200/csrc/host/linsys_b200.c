@@ -98,11 +98,65 @@ static int expand_sym_upper(int n, const int *Pp, const int *Pi, const double *P
   return 0;
 }
 
+/* Row partition for the sharded KKT solve: contiguous blocks with (nearly) equal
+ * numbers of nonzeros. */
+void b200_row_partition(int m, int n, const int *Ap, const int *Ai, int nranks, int *offsets) {
+  const long long nnz = Ap[n];
+  long long *cnt = (long long *)calloc((size_t)m + 1, sizeof(long long));
+  long long acc = 0;
+  int i, r = 1;
+  offsets[0] = 0;
+  if (!cnt) { /* fall back to equal rows */
+    for (r = 1; r <= nranks; ++r) offsets[r] = (int)(((long long)m * r) / nranks);
+    return;
+  }
+  for (i = 0; i < nnz; ++i) cnt[Ai[i]]++;
+  for (i = 0; i < m && r < nranks; ++i) {
+    acc += cnt[i] + 1; /* +1: empty rows still cost a row */
+    while (r < nranks && acc >= ((nnz + m) * (long long)r) / nranks) offsets[r++] = i + 1;
+  }
+  while (r <= nranks) offsets[r++] = m;
+  offsets[nranks] = m;
+  free(cnt);
+}
+scs_int scs_b200_row_partition(scs_int m, scs_int n, const scs_int *Ap, const scs_int *Ai,
+                               scs_int nranks, scs_int *offsets) {
+  if (m <= 0 || n <= 0 || nranks <= 0 || !Ap || !Ai || !offsets) return -1;
+  b200_row_partition(m, n, Ap, Ai, nranks, offsets);
+  return 0;
+}
+
+/* CSC restricted to rows [r0, r1), row indices shifted by -r0 */
+static int restrict_rows(int n, const int *Ap, const int *Ai, const double *Ax, int r0, int r1,
+                         int **Lp_out, int **Li_out, double **Lx_out) {
+  int j, k, cnt = 0;
+  int *Lp = (int *)calloc((size_t)n + 1, sizeof(int));
+  int *Li;
+  double *Lx;
+  if (!Lp) return -1;
+  for (j = 0; j < n; ++j) {
+    for (k = Ap[j]; k < Ap[j + 1]; ++k)
+      if (Ai[k] >= r0 && Ai[k] < r1) cnt++;
+    Lp[j + 1] = cnt;
+  }
+  Li = (int *)malloc(((size_t)cnt + 1) * sizeof(int));
+  Lx = (double *)malloc(((size_t)cnt + 1) * sizeof(double));
+  if (!Li || !Lx) { free(Lp); free(Li); free(Lx); return -1; }
+  cnt = 0;
+  for (j = 0; j < n; ++j)
+    for (k = Ap[j]; k < Ap[j + 1]; ++k)
+      if (Ai[k] >= r0 && Ai[k] < r1) { Li[cnt] = Ai[k] - r0; Lx[cnt] = Ax[k]; cnt++; }
+  *Lp_out = Lp; *Li_out = Li; *Lx_out = Lx;
+  return 0;
+}
+
 ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
                                      const scs_float *diag_r) {
   ScsLinSysWork *w;
   int *Tp = NULL, *Ti = NULL;
   double *Tx = NULL;
+  int *Lp = NULL, *Li = NULL;
+  double *Lx = NULL;
   const int n = A->n, m = A->m;
   if (b200_runtime_init() != 0) {
     fprintf(stderr, "scs_b200: no usable sm_100 device: %s\n", b200_last_error());
@@ -112,10 +166,28 @@ ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
   if (!w) return SCS_NULL;
   w->n = n; w->m = m;
   w->nnz = A->p[n];
-  /* CSR of A' is the CSC of A as given */
-  w->At = b200_spmv_create(n, m, A->p, A->i, A->x);
-  if (transpose_csc(m, n, A->p, A->i, A->x, &Tp, &Ti, &Tx) != 0) goto fail;
-  w->A = b200_spmv_create(m, n, Tp, Ti, Tx);
+  w->nranks = b200_comm_nranks();
+  w->rank = b200_comm_rank();
+  w->row0 = 0;
+  w->mloc = m;
+  if (w->nranks > 1) {
+    /* row-sharded: keep only rows [row0, row0+mloc) of A, in both orientations */
+    w->offsets = (int *)calloc((size_t)w->nranks + 1, sizeof(int));
+    if (!w->offsets) goto fail;
+    b200_row_partition(m, n, A->p, A->i, w->nranks, w->offsets);
+    w->row0 = w->offsets[w->rank];
+    w->mloc = w->offsets[w->rank + 1] - w->row0;
+    if (restrict_rows(n, A->p, A->i, A->x, w->row0, w->row0 + w->mloc, &Lp, &Li, &Lx) != 0) goto fail;
+    w->At = b200_spmv_create(n, w->mloc, Lp, Li, Lx);
+    if (transpose_csc(w->mloc, n, Lp, Li, Lx, &Tp, &Ti, &Tx) != 0) { free(Lp); free(Li); free(Lx); goto fail; }
+    w->A = b200_spmv_create(w->mloc, n, Tp, Ti, Tx);
+    free(Lp); free(Li); free(Lx);
+  } else {
+    /* CSR of A' is the CSC of A as given */
+    w->At = b200_spmv_create(n, m, A->p, A->i, A->x);
+    if (transpose_csc(m, n, A->p, A->i, A->x, &Tp, &Ti, &Tx) != 0) goto fail;
+    w->A = b200_spmv_create(m, n, Tp, Ti, Tx);
+  }
   free(Tp); free(Ti); free(Tx);
   if (!w->A || !w->At) goto fail;
   if (P) {
@@ -144,10 +216,11 @@ ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
   w->cg.d_ctl = (B200CgCtl *)b200_malloc(sizeof(B200CgCtl));
   w->cg.d_partials = (double *)b200_malloc(4 * 2048 * 8);
   w->cg.d_counter = (unsigned int *)b200_malloc(64);
+  w->cg.d_red = (double *)b200_malloc((size_t)n * 8);
   w->cg.h_ctl = (B200CgCtl *)b200_host_alloc(sizeof(B200CgCtl));
   if (!w->d_diag_r || !w->d_b || !w->d_s || !w->cg.d_M || !w->cg.d_p || !w->cg.d_r ||
       !w->cg.d_Gp || !w->cg.d_z || !w->cg.d_tmp || !w->cg.d_ctl || !w->cg.d_partials ||
-      !w->cg.d_counter || !w->cg.h_ctl)
+      !w->cg.d_counter || !w->cg.h_ctl || !w->cg.d_red)
     goto fail;
   b200_memset0(w->cg.d_counter, 64);
   b200_memset0(w->cg.d_ctl, sizeof(B200CgCtl));
@@ -156,6 +229,7 @@ ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
   w->cg.A = w->A; w->cg.At = w->At; w->cg.P = w->P;
   w->cg.d_rx = w->d_diag_r;
   w->cg.d_ry = w->d_diag_r + n;
+  w->cg.nranks = w->nranks; w->cg.row0 = w->row0; w->cg.mloc = w->mloc; w->cg.offsets = w->offsets;
   if (b200_h2d(w->d_diag_r, diag_r, ((size_t)n + m) * 8) != 0) goto fail;
   if (b200_cg_set_preconditioner(&w->cg, w->d_Pdiag) != 0) goto fail;
   if (b200_sync() != 0) goto fail;
@@ -185,7 +259,9 @@ void scs_free_lin_sys_work(ScsLinSysWork *w) {
   b200_free(w->cg.d_ctl);
   b200_free(w->cg.d_partials);
   b200_free(w->cg.d_counter);
+  b200_free(w->cg.d_red);
   b200_host_free(w->cg.h_ctl);
+  free(w->offsets);
   free(w);
 }
 
@@ -239,7 +315,7 @@ static scs_int accum_generic(ScsLinSysWork *w, const B200Spmv *M, int ncols, int
   double *d_x = (double *)b200_malloc((size_t)ncols * 8);
   double *d_y = (double *)b200_malloc((size_t)nrows * 8);
   int rc = -1;
-  (void)w;
+  if (w->nranks > 1) { b200_free(d_x); b200_free(d_y); return -1; } /* operator-level API is single-GPU */
   if (!d_x || !d_y) goto out;
   if (b200_h2d(d_x, x, (size_t)ncols * 8) != 0) goto out;
   if (accumulate && b200_h2d(d_y, y, (size_t)nrows * 8) != 0) goto out;

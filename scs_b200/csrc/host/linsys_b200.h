@@ -17,6 +17,9 @@ struct SCS_LIN_SYS_WORK {
   double *d_b;      /* staging for the host-pointer plugin call (n+m) */
   double *d_s;      /* staging for the warm start (n) */
   B200Cg cg;
+  /* row-sharded mode: this rank owns rows [row0, row0+mloc); offsets has nranks+1 entries */
+  int nranks, rank, row0, mloc;
+  int *offsets;
   int last_cg_its;
   long long tot_cg_its;
   long long n_solves;
@@ -26,5 +29,7 @@ struct SCS_LIN_SYS_WORK {
 int b200_linsys_solve_dev(ScsLinSysWork *w, double *d_b, const double *d_s, double tol,
                           const double *d_tol);
 int b200_linsys_update_diag_r_dev(ScsLinSysWork *w, const double *d_diag_r);
+/* contiguous row blocks balanced by nonzeros; offsets[nranks+1] (also exported for the tests) */
+void b200_row_partition(int m, int n, const int *Ap, const int *Ai, int nranks, int *offsets);
 
 #endif

@@ -484,12 +484,14 @@ static int populate_residual_struct(ScsWork *w, int iter) {
   r->last_iter = iter;
   memset(&a, 0, sizeof(a));
   a.init_sign = 1.0; a.post = B200_POST_NONE; a.hook = B200_HOOK_NONE;
-  /* ax = A x */
-  a.d_x = w->adm.d_u; a.d_y = w->d_ax;
+  /* ax = A x (row-sharded: local rows, then all-gather) */
+  a.d_x = w->adm.d_u; a.d_y = w->d_ax + w->p->row0;
   if (b200_spmv(w->p->A, &a) != 0) return -1;
-  /* aty = A' y */
-  a.d_x = w->adm.d_u + n; a.d_y = w->d_aty;
+  if (w->p->nranks > 1 && b200_allgatherv(w->d_ax, w->p->offsets) != 0) return -1;
+  /* aty = A' y (row-sharded: local partial, then all-reduce) */
+  a.d_x = w->adm.d_u + n + w->p->row0; a.d_y = w->d_aty;
   if (b200_spmv(w->p->At, &a) != 0) return -1;
+  if (w->p->nranks > 1 && b200_allreduce_sum(w->d_aty, (size_t)n) != 0) return -1;
   if (w->p->P) {
     a.d_x = w->adm.d_u; a.d_y = w->d_px;
     if (b200_spmv(w->p->P, &a) != 0) return -1;
@@ -928,7 +930,7 @@ scs_int scs_b200_get_stats(const ScsWork *w, ScsB200Stats *out) {
   out->lin_sys_solves = w->stat_solves;
   out->kernel_launches = w->stat_launches;
   out->spmv_ms = 0.0;
-  out->n_gpus = 1;
+  out->n_gpus = b200_comm_nranks();
   return 0;
 }
 scs_int scs_b200_set_max_iters(ScsWork *w, scs_int max_iters) {

@@ -21,6 +21,7 @@
 #include "../common.cuh"
 #include "../dev_api.h"
 #include <math.h>
+#include <string.h>
 
 #define VEC_THREADS B200_RED_THREADS
 
@@ -234,8 +235,73 @@ __global__ void k_zero_if(long long len, double *__restrict__ v, const int *flag
 }
 
 // ---------------------------------------------------------------------------
+// Row-sharded mode: every rank holds rows [row0, row0+mloc) of A in both
+// orientations; x-space vectors are replicated. A' R_y^-1 A p is the sum over ranks of the
+// local partial products -> one all-reduce of an n-vector per CG iteration; every other
+// quantity (dots, alpha, beta, stop test) is then computed redundantly and bit-identically
+// on every rank, so no scalar collective is needed.
+__global__ void __launch_bounds__(VEC_THREADS)
+k_cg_finish_mv(int n, double *__restrict__ y, const double *__restrict__ red, int y_has_px,
+               const double *__restrict__ rx, const double *__restrict__ x, int with_dot,
+               B200CgCtl *ctl, const int *skip, double *partials, unsigned int *counter) {
+  if (skip != nullptr && *skip) return;
+  __shared__ double s_red[64];
+  double acc[1] = {0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double base = y_has_px ? y[i] + red[i] : red[i];
+    const double xi = x[i];
+    const double out = fma(rx[i], xi, base);
+    y[i] = out;
+    acc[0] = fma(xi, out, acc[0]);
+  }
+  if (!with_dot) return;
+  block_sum<1>(acc, s_red);
+  if (grid_finish<1>(acc, partials, counter, 0u, s_red)) {
+    if (threadIdx.x == 0) {
+      ctl->pGp = acc[0];
+      ctl->alpha = ctl->ztr / acc[0];
+    }
+  }
+}
+__global__ void k_add_if_not(int n, double *__restrict__ a, const double *__restrict__ b, const int *skip) {
+  if (skip != nullptr && *skip) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a[i] += b[i];
+}
+// M = 1 / (R_x + P_jj + sum over ALL ranks of the local column sums)
+__global__ void k_precond_partial(int n, const int *__restrict__ colptr, const int *__restrict__ rowidx,
+                                  const double *__restrict__ vals, const double *__restrict__ ry_loc,
+                                  double *__restrict__ out) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int k = colptr[j]; k < colptr[j + 1]; ++k) {
+      const double v = vals[k];
+      acc += v * v / ry_loc[rowidx[k]];
+    }
+    out[j] = acc;
+  }
+}
+__global__ void k_precond_finish(int n, const double *__restrict__ rx, const double *__restrict__ sum,
+                                 const double *__restrict__ pdiag, double *__restrict__ M) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    double acc = rx[j] + sum[j];
+    if (pdiag != nullptr) acc += pdiag[j];
+    M[j] = 1.0 / acc;
+  }
+}
+
+// ---------------------------------------------------------------------------
 extern "C" int b200_cg_set_preconditioner(const B200Cg *cg, const double *d_Pdiag) {
   cudaStream_t st = (cudaStream_t)b200_stream();
+  if (cg->nranks > 1) {
+    k_precond_partial<<<vec_grid(cg->n), 256, 0, st>>>(cg->n, b200_spmv_rowptr(cg->At),
+                                                      b200_spmv_colidx(cg->At), b200_spmv_vals(cg->At),
+                                                      cg->d_ry + cg->row0, cg->d_red);
+    if (b200_allreduce_sum(cg->d_red, (size_t)cg->n) != 0) return -1;
+    k_precond_finish<<<vec_grid(cg->n), 256, 0, st>>>(cg->n, cg->d_rx, cg->d_red, d_Pdiag, cg->d_M);
+    b200_count_launch(2);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   // CSR of A' == CSC of A: rowptr = column pointers, colidx = row indices
   k_set_preconditioner<<<vec_grid(cg->n), 256, 0, st>>>(
       cg->n, b200_spmv_rowptr(cg->At), b200_spmv_colidx(cg->At), b200_spmv_vals(cg->At), cg->d_rx,
@@ -246,7 +312,33 @@ extern "C" int b200_cg_set_preconditioner(const B200Cg *cg, const double *d_Pdia
 }
 
 // y = (R_x + P + A' R_y^-1 A) x   (private.c:106-119); dot/hook optional
+static int mat_vec_sharded(B200Cg *cg, const double *d_x, double *d_y, int with_dot,
+                           const int *d_skip) {
+  cudaStream_t st = (cudaStream_t)b200_stream();
+  B200SpmvArgs a;
+  memset(&a, 0, sizeof(a));
+  // K1 (local rows): tmp[row0:row0+mloc] = (A_g x) ./ R_y
+  a.d_x = d_x; a.d_y = cg->d_tmp + cg->row0; a.init_sign = 1.0; a.post = B200_POST_DIV;
+  a.d_d = cg->d_ry + cg->row0; a.d_skip = d_skip;
+  if (b200_spmv(cg->A, &a) != 0) return -1;
+  // local partial  red = A_g' tmp_g ; sum over ranks
+  a.d_x = cg->d_tmp + cg->row0; a.d_y = cg->d_red; a.post = B200_POST_NONE; a.d_d = nullptr;
+  if (b200_spmv(cg->At, &a) != 0) return -1;
+  if (b200_allreduce_sum(cg->d_red, (size_t)cg->n) != 0) return -1;
+  if (cg->P) {  // P is replicated
+    a.d_x = d_x; a.d_y = d_y;
+    if (b200_spmv(cg->P, &a) != 0) return -1;
+  }
+  int g = (cg->n + VEC_THREADS * 4 - 1) / (VEC_THREADS * 4);
+  if (g > 2 * b200_num_sms()) g = 2 * b200_num_sms();
+  k_cg_finish_mv<<<g, VEC_THREADS, 0, st>>>(cg->n, d_y, cg->d_red, cg->P != nullptr, cg->d_rx, d_x,
+                                            with_dot, cg->d_ctl, d_skip, cg->d_partials, cg->d_counter);
+  b200_count_launch(1);
+  return 0;
+}
+
 static int mat_vec(B200Cg *cg, const double *d_x, double *d_y, int with_dot, const int *d_skip) {
+  if (cg->nranks > 1) return mat_vec_sharded(cg, d_x, d_y, with_dot, d_skip);
   B200SpmvArgs a;
   // K1: tmp = (A x) ./ R_y
   a.d_x = d_x; a.d_y = cg->d_tmp; a.d_init = nullptr; a.init_sign = 1.0;
@@ -304,7 +396,16 @@ extern "C" int b200_cg_solve(B200Cg *cg, double *d_b, const double *d_s, double 
       cg->d_counter);
   b200_count_launch(1);
   // b[0:n] += A' tmp   (private.c:305)
-  {
+  if (cg->nranks > 1) {
+    B200SpmvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.d_x = cg->d_tmp + cg->row0; a.d_y = cg->d_red; a.init_sign = 1.0; a.post = B200_POST_NONE;
+    a.d_skip = d_skip;
+    if (b200_spmv(cg->At, &a) != 0) return -1;
+    if (b200_allreduce_sum(cg->d_red, (size_t)n) != 0) return -1;
+    k_add_if_not<<<g, VEC_THREADS, 0, st>>>(n, d_b, cg->d_red, d_skip);
+    b200_count_launch(1);
+  } else {
     B200SpmvArgs a;
     a.d_x = cg->d_tmp; a.d_y = d_b; a.d_init = d_b; a.init_sign = 1.0; a.post = B200_POST_NONE;
     a.d_d = nullptr; a.d_v = nullptr; a.d_dot = nullptr; a.hook = B200_HOOK_NONE;
@@ -336,7 +437,15 @@ extern "C" int b200_cg_solve(B200Cg *cg, double *d_b, const double *d_s, double 
     batch = batch < 16 ? 16 : (batch < 64 ? batch * 2 : 64);
   }
   // y = R_y^{-1} (A x - r_y)   (private.c:313-317)
-  {
+  if (cg->nranks > 1) {
+    B200SpmvArgs a;
+    memset(&a, 0, sizeof(a));
+    double *yl = d_b + n + cg->row0;
+    a.d_x = d_b; a.d_y = yl; a.d_init = yl; a.init_sign = -1.0; a.post = B200_POST_DIV;
+    a.d_d = cg->d_ry + cg->row0; a.d_skip = d_skip;
+    if (b200_spmv(cg->A, &a) != 0) return -1;
+    if (b200_allgatherv(d_b + n, cg->offsets) != 0) return -1;
+  } else {
     B200SpmvArgs a;
     a.d_x = d_b; a.d_y = d_b + n; a.d_init = d_b + n; a.init_sign = -1.0; a.post = B200_POST_DIV;
     a.d_d = cg->d_ry; a.d_v = nullptr; a.d_dot = nullptr; a.hook = B200_HOOK_NONE;

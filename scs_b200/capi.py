@@ -15,7 +15,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscs_b200.so")
+LIB_PATH = os.environ.get("SCS_B200_LIB", os.path.join(_HERE, "libscs_b200.so"))
 
 c_int_p = C.POINTER(C.c_int)
 c_double_p = C.POINTER(C.c_double)
@@ -241,6 +241,13 @@ def _declare(lib, ours):
     lib.scs_b200_get_stats.argtypes = [C.c_void_p, C.POINTER(ScsB200Stats)]
     lib.scs_b200_set_max_iters.restype = C.c_int
     lib.scs_b200_set_max_iters.argtypes = [C.c_void_p, C.c_int]
+    lib.scs_b200_comm_unique_id.restype = C.c_int
+    lib.scs_b200_comm_unique_id.argtypes = [C.c_char_p]
+    lib.scs_b200_comm_init.restype = C.c_int
+    lib.scs_b200_comm_init.argtypes = [C.c_int, C.c_int, C.c_char_p]
+    lib.scs_b200_comm_finalize.restype = C.c_int
+    lib.scs_b200_row_partition.restype = C.c_int
+    lib.scs_b200_row_partition.argtypes = [C.c_int, C.c_int, c_int_p, c_int_p, C.c_int, c_int_p]
     lib.scs_b200_launch_count.restype = C.c_longlong
     lib.scs_b200_device_ok.restype = C.c_int
 

@@ -70,6 +70,12 @@ int b200_vec_scale(long long len, double *d_a, double f);
 int b200_vec_fill(long long len, double *d_a, double f);
 int b200_vec_scale_by(long long len, double *d_a, const double *d_d, double f);
 
+/* ---------------------------------------------------------------- equilibration (kernels/equil.cu) */
+/* Ruiz + L2 equilibration in place on both resident orientations of A (P = 0). bnd[0] = z+l+bsize,
+ * bnd[1..nbnd) = sizes of the cones sharing one D value. d_D (m), d_E (n) are outputs. */
+int b200_equilibrate_dev(B200Spmv *A_rows, B200Spmv *A_cols, const int *bnd, int nbnd, double *d_D,
+                         double *d_E);
+
 /* ---------------------------------------------------------------- cones (kernels/cones.cu) */
 typedef struct B200Cones B200Cones;
 /* k_* arrays are HOST arrays; box bounds already scaled (normalize_box_cone). */

@@ -43,6 +43,7 @@ typedef struct {
 
 struct SCS_WORK {
   int n, m;
+  long long nnzA, nnzP;
   double setup_time;
   int time_limit_reached;
   /* host copies */

@@ -314,13 +314,13 @@ static void print_header(const ScsWork *w) {
     printf("\t  acceleration_lookback: %i, acceleration_interval: %i\n",
            w->stgs->acceleration_lookback, w->stgs->acceleration_interval);
   printf("lin-sys:  %s\n\t  nnz(A): %li, nnz(P): %li\n", scs_get_lin_sys_method(),
-         (long)w->d->A->p[w->n], w->d->P ? (long)w->d->P->p[w->n] : 0l);
+         (long)w->nnzA, (long)w->nnzP);
 }
 
 ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {
   ScsWork *w;
   const double t0 = now_ms();
-  int n, m, i;
+  int n, m, i, dev_equil = 0;
   size_t l;
   if (!d || !k || !stgs) {
     printf("ERROR: Missing ScsData, ScsCone, or ScsSettings input\n");
@@ -347,11 +347,17 @@ ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {
   w->stgs = (ScsSettings *)calloc(1, sizeof(ScsSettings));
   if (!w->d || !w->k || !w->stgs) goto fail;
   w->d->n = n; w->d->m = m;
-  w->d->A = copy_matrix(d->A);
+  w->nnzA = d->A->p[n];
+  w->nnzP = d->P ? d->P->p[n] : 0;
+  /* Equilibrate on the device when possible (P = 0, single GPU): the user's A is uploaded as
+   * is and both resident orientations are rescaled in place (kernels/equil.cu), so no host
+   * copy of A is needed at all. Otherwise (P != 0 or row-sharded) equilibrate a host copy. */
+  dev_equil = stgs->normalize && !d->P && b200_comm_nranks() == 1 && !getenv("SCS_B200_HOST_EQUIL");
+  w->d->A = dev_equil ? SCS_NULL : copy_matrix(d->A);
   w->d->P = d->P ? copy_matrix(d->P) : SCS_NULL;
   w->d->b = (double *)dup_mem(d->b, (size_t)m * 8);
   w->d->c = (double *)dup_mem(d->c, (size_t)n * 8);
-  if (!w->d->A || (d->P && !w->d->P) || !w->d->b || !w->d->c) goto fail;
+  if ((!dev_equil && !w->d->A) || (d->P && !w->d->P) || !w->d->b || !w->d->c) goto fail;
   *w->k = *k;
   w->k->bu = w->k->bl = SCS_NULL; w->k->q = SCS_NULL; w->k->s = SCS_NULL;
   w->k->cs = SCS_NULL; w->k->p = SCS_NULL;
@@ -380,9 +386,11 @@ ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {
     w->D = (double *)malloc((size_t)m * 8);
     w->E = (double *)malloc((size_t)n * 8);
     if (!w->D || !w->E) goto fail;
-    if (b200_equilibrate(w->d->P, w->d->A, w->cone_boundaries, w->cone_boundaries_len, w->D, w->E) != 0)
-      goto fail;
-    if (w->k->bsize > 1) normalize_box_cone(w->k, w->D + w->k->z + w->k->l, w->k->bsize);
+    if (!dev_equil) {
+      if (b200_equilibrate(w->d->P, w->d->A, w->cone_boundaries, w->cone_boundaries_len, w->D, w->E) != 0)
+        goto fail;
+      if (w->k->bsize > 1) normalize_box_cone(w->k, w->D + w->k->z + w->k->l, w->k->bsize);
+    }
   }
 
   /* device state */
@@ -428,10 +436,25 @@ ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {
     w->d_D = (double *)b200_malloc((size_t)m * 8);
     w->d_E = (double *)b200_malloc((size_t)n * 8);
     if (!w->d_D || !w->d_E) goto fail;
-    i |= b200_h2d(w->d_D, w->D, (size_t)m * 8);
-    i |= b200_h2d(w->d_E, w->E, (size_t)n * 8);
+    if (!dev_equil) {
+      i |= b200_h2d(w->d_D, w->D, (size_t)m * 8);
+      i |= b200_h2d(w->d_E, w->E, (size_t)n * 8);
+    }
   }
   if (i != 0) goto fail;
+  if (dev_equil) {
+    /* upload the raw A (both orientations), equilibrate in place on the device */
+    w->p = scs_init_lin_sys_work(d->A, SCS_NULL, w->h_diag_r);
+    if (!w->p) { printf("ERROR: init_lin_sys_work failure\n"); goto fail; }
+    if (b200_equilibrate_dev(w->p->A, w->p->At, w->cone_boundaries, w->cone_boundaries_len, w->d_D,
+                             w->d_E) != 0)
+      goto fail;
+    if (b200_linsys_update_diag_r_dev(w->p, w->p->d_diag_r) != 0) goto fail; /* preconditioner of D A E */
+    if (b200_d2h(w->D, w->d_D, (size_t)m * 8) != 0 || b200_d2h(w->E, w->d_E, (size_t)n * 8) != 0 ||
+        b200_sync() != 0)
+      goto fail;
+    if (w->k->bsize > 1) normalize_box_cone(w->k, w->D + w->k->z + w->k->l, w->k->bsize);
+  }
   /* b, c: stores *_orig, normalises, uploads */
   memcpy(w->b_orig, d->b, (size_t)m * 8);
   memcpy(w->c_orig, d->c, (size_t)n * 8);
@@ -440,7 +463,7 @@ ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {
   w->cones = b200_cones_create(m, w->k->z, w->k->l, w->k->bsize, w->k->bl, w->k->bu, w->k->qsize,
                                w->k->q, w->k->ssize, w->k->s);
   if (!w->cones) { printf("ERROR: init_cone failure\n"); goto fail; }
-  w->p = scs_init_lin_sys_work(w->d->A, w->d->P, w->h_diag_r);
+  if (!w->p) w->p = scs_init_lin_sys_work(w->d->A, w->d->P, w->h_diag_r);
   if (!w->p) { printf("ERROR: init_lin_sys_work failure\n"); goto fail; }
   if (w->stgs->acceleration_lookback) {
     w->accel = b200_aa_create((int)l, w->stgs->acceleration_lookback, w->stgs->acceleration_lookback,

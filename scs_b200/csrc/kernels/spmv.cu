@@ -33,11 +33,26 @@
 #include <string.h>
 #include <vector>
 
+// tuning knobs (overridable with -D for sweeps; see profiles/README.md for the measurements)
+#ifndef SPMV_DEFAULT_VERSION
+#define SPMV_DEFAULT_VERSION 2  // warp-specialised pipeline (SCS_B200_SPMV=1 selects the two-phase kernel)
+#endif
+#ifndef SPMV_THREADS
 #define SPMV_THREADS 512
+#endif
+#ifndef SPMV_STAGES
 #define SPMV_STAGES 3
+#endif
+#ifndef SPMV_TILE_NNZ
 #define SPMV_TILE_NNZ 2048
+#endif
+#ifndef SPMV_CTAS_PER_SM
+#define SPMV_CTAS_PER_SM 2
+#endif
 #define SPMV_TILE_CAP (SPMV_TILE_NNZ + 8)
-#define SPMV_TILE_ROWS 1024
+#ifndef SPMV_TILE_ROWS
+#define SPMV_TILE_ROWS (SPMV_TILE_NNZ / 2)
+#endif
 #define SPMV_GATHERS (SPMV_TILE_NNZ / SPMV_THREADS)  // independent gathers per thread in flight
 
 // tile descriptor: x=row0, y=nrows | (type<<28) | (lg_lanes<<24), z=k0, w=nnz
@@ -60,6 +75,7 @@ struct B200Spmv {
   int tile_nnz;
   double *d_partials;
   unsigned int *d_counter;
+  int version;  // 1: two-phase block kernel, 2: warp-specialised pipeline
 };
 
 static size_t spmv_smem_bytes() {
@@ -81,6 +97,33 @@ __device__ __forceinline__ void spmv_issue_tile(const int4 t, int stage, double 
   }
 }
 
+// random 8-byte gather of the dense vector: read-only path, optionally without L1 allocation
+__device__ __forceinline__ double gather_ld(const double *p) {
+#ifdef SPMV_GATHER_NOALLOC
+  double r;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+#else
+  return __ldg(p);
+#endif
+}
+// epilogue with operands fetched EARLY (before the gathers are consumed) so that their latency
+// overlaps the row's chain instead of adding to it
+template <int POST>
+__device__ __forceinline__ void spmv_epilogue_pre(double s, int row, double *__restrict__ y, double dv,
+                                                  double vv, double &dot_acc) {
+  double out = s;
+  if (POST == B200_POST_DIV) {
+    out = s / dv;
+  } else if (POST == B200_POST_FMA_DOT) {
+    out = fma(dv, vv, s);
+    dot_acc = fma(vv, out, dot_acc);
+  } else if (POST == B200_POST_FMA) {
+    out = fma(dv, vv, s);
+  }
+  y[row] = out;
+}
+
 template <int POST>
 __device__ __forceinline__ double spmv_epilogue(double s, int row, double *__restrict__ y,
                                                 const double *__restrict__ d,
@@ -100,7 +143,7 @@ __device__ __forceinline__ double spmv_epilogue(double s, int row, double *__res
 }
 
 template <int POST>
-__global__ void __launch_bounds__(SPMV_THREADS, 2)
+__global__ void __launch_bounds__(SPMV_THREADS, SPMV_CTAS_PER_SM)
 spmv_csr_stream_kernel(const int *__restrict__ rowptr, const int *__restrict__ colidx,
                        const double *__restrict__ vals, const int4 *__restrict__ tiles,
                        const int *__restrict__ cta_tile_begin, const double *__restrict__ x,
@@ -257,6 +300,180 @@ spmv_csr_stream_kernel(const int *__restrict__ rowptr, const int *__restrict__ c
   }
 }
 
+// ==================================================================================
+// Version 2: warp-specialised pipeline.  Warp 0 is the TMA PRODUCER (one elected lane issues
+// the bulk copies of the value / column-index / row-pointer slices of tile i+S as soon as the
+// consumers have released the stage); warps 1..NW-1 are CONSUMERS: each takes rows of the tile
+// (one row per thread for short rows), gathers x straight from global memory with up to 8
+// independent loads in flight per thread, and adds the products in storage order (bit-identical
+// to the sequential CPU loop).  Stages are handed over with full/empty mbarriers only -- there
+// is no __syncthreads in the main loop, so a fast warp runs ahead into the next tile.
+// defaults from the sweep in profiles/README.md (C2, B200): 512 threads (1 producer + 15 consumer
+// warps), 1536-entry tiles, 3 stages, 2 CTAs/SM = 148 kB of shared memory per SM, which leaves
+// ~80 kB of L1 for the gathers (bigger tiles / more stages shrink L1 and lose more than they gain)
+#ifndef SPMV2_THREADS
+#define SPMV2_THREADS 512
+#endif
+#ifndef SPMV2_STAGES
+#define SPMV2_STAGES 3
+#endif
+#ifndef SPMV2_TILE_NNZ
+#define SPMV2_TILE_NNZ 1536
+#endif
+#ifndef SPMV2_CTAS_PER_SM
+#define SPMV2_CTAS_PER_SM 2
+#endif
+#define SPMV2_TILE_ROWS SPMV2_TILE_NNZ
+#define SPMV2_CAP (SPMV2_TILE_NNZ + 8)
+#define SPMV2_RCAP (SPMV2_TILE_ROWS + 8)
+#define SPMV2_NCW (SPMV2_THREADS / 32 - 1)
+#define SPMV2_CHUNK 8
+
+static size_t spmv2_smem_bytes() {
+  return (size_t)SPMV2_STAGES * (SPMV2_CAP * 12 + SPMV2_RCAP * 4) + 2 * SPMV2_STAGES * 8 + 64 * 8;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int POST>
+__global__ void __launch_bounds__(SPMV2_THREADS, SPMV2_CTAS_PER_SM)
+spmv_ws_kernel(const int *__restrict__ rowptr, const int *__restrict__ colidx,
+               const double *__restrict__ vals, const int4 *__restrict__ tiles,
+               const int *__restrict__ cta_tile_begin, const double *__restrict__ x,
+               double *__restrict__ y, const double *init, double init_sign,
+               const double *__restrict__ d, const double *__restrict__ v, double *dot_out, int hook,
+               void *hook_arg, const int *skip, double *partials, unsigned int *counter) {
+  if (skip != nullptr && *((volatile const int *)skip) != 0) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *s_vals = reinterpret_cast<double *>(smem_raw);
+  int *s_idx = reinterpret_cast<int *>(s_vals + SPMV2_STAGES * SPMV2_CAP);
+  int *s_rp = s_idx + SPMV2_STAGES * SPMV2_CAP;
+  uint64_t *s_full = reinterpret_cast<uint64_t *>(s_rp + SPMV2_STAGES * SPMV2_RCAP);
+  uint64_t *s_empty = s_full + SPMV2_STAGES;
+  double *s_red = reinterpret_cast<double *>(s_empty + SPMV2_STAGES);
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int t_begin = cta_tile_begin[blockIdx.x];
+  const int nt = cta_tile_begin[blockIdx.x + 1] - t_begin;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < SPMV2_STAGES; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], SPMV2_NCW);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  double dot_acc = 0.0;
+  if (wid == 0) {
+    // ------------------------------------------------ producer
+    if (lane == 0) {
+      const uint64_t pol = l2_policy_evict_first();
+      for (int i = 0; i < nt; ++i) {
+        const int st = i % SPMV2_STAGES, use = i / SPMV2_STAGES;
+        if (use > 0) mbar_wait(&s_empty[st], (unsigned)((use - 1) & 1));
+        const int4 t = tiles[t_begin + i];
+        const int k0 = t.z, nnz = t.w, row0 = t.x;
+        const int nrows = t.y & 0x00ffffff, type = (t.y >> 28) & 0x7;
+        const int ka = k0 & ~3;
+        const int cnt = (k0 + nnz - ka + 3) & ~3;
+        const int ra = row0 & ~3;
+        const int rcnt = (type == TILE_NORMAL) ? ((row0 + nrows + 1 - ra + 3) & ~3) : 0;
+        mbar_expect_tx(&s_full[st], (unsigned)cnt * 12u + (unsigned)rcnt * 4u);
+        if (cnt > 0) {
+          tma_load_1d(s_vals + (size_t)st * SPMV2_CAP, vals + ka, (unsigned)cnt * 8u, &s_full[st], pol);
+          tma_load_1d(s_idx + (size_t)st * SPMV2_CAP, colidx + ka, (unsigned)cnt * 4u, &s_full[st], pol);
+        }
+        if (rcnt > 0)
+          tma_load_1d(s_rp + (size_t)st * SPMV2_RCAP, rowptr + ra, (unsigned)rcnt * 4u, &s_full[st], pol);
+      }
+    }
+  } else {
+    // ------------------------------------------------ consumers
+    const int cw = wid - 1;
+    double carry = 0.0;  // long-row running sum (consumer warp 0, lane 0)
+    for (int i = 0; i < nt; ++i) {
+      const int st = i % SPMV2_STAGES;
+      const unsigned par = (unsigned)((i / SPMV2_STAGES) & 1);
+      const int4 t = tiles[t_begin + i];
+      const int row0 = t.x, nrows = t.y & 0x00ffffff, lg = (t.y >> 24) & 0xf, type = (t.y >> 28) & 0x7;
+      const int k0 = t.z, nnz = t.w;
+      const double *__restrict__ tv = s_vals + (size_t)st * SPMV2_CAP + (k0 & 3);
+      const int *__restrict__ ti = s_idx + (size_t)st * SPMV2_CAP + (k0 & 3);
+      const int *__restrict__ rp = s_rp + (size_t)st * SPMV2_RCAP + (row0 & 3);
+      mbar_wait(&s_full[st], par);
+      if (type == TILE_NORMAL && lg == 0) {
+        for (int r = cw * 32 + lane; r < nrows; r += SPMV2_NCW * 32) {
+          const int row = row0 + r;
+          const int a = rp[r] - k0, b = rp[r + 1] - k0;
+          // epilogue operands first: their (global) latency overlaps the gathers below
+          const double dv = (POST != B200_POST_NONE) ? d[row] : 0.0;
+          const double ev = (POST == B200_POST_FMA_DOT || POST == B200_POST_FMA) ? v[row] : 0.0;
+          double s = (init != nullptr) ? init_sign * init[row] : 0.0;
+          for (int k = a; k < b; k += SPMV2_CHUNK) {
+            int c[SPMV2_CHUNK];
+            double xv[SPMV2_CHUNK], vv[SPMV2_CHUNK];
+#pragma unroll
+            for (int u = 0; u < SPMV2_CHUNK; ++u) c[u] = (k + u < b) ? ti[k + u] : -1;
+#pragma unroll
+            for (int u = 0; u < SPMV2_CHUNK; ++u) xv[u] = (c[u] >= 0) ? gather_ld(&x[c[u]]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < SPMV2_CHUNK; ++u) vv[u] = (c[u] >= 0) ? tv[k + u] : 0.0;
+#pragma unroll
+            for (int u = 0; u < SPMV2_CHUNK; ++u)
+              if (c[u] >= 0) s = __dadd_rn(s, __dmul_rn(vv[u], xv[u]));
+          }
+          spmv_epilogue_pre<POST>(s, row, y, dv, ev, dot_acc);
+        }
+      } else if (type == TILE_NORMAL) {
+        // longer rows: one warp per row, lanes stride the entries, fixed shuffle tree
+        for (int r = cw; r < nrows; r += SPMV2_NCW) {
+          const int row = row0 + r;
+          const int a = rp[r] - k0, b = rp[r + 1] - k0;
+          double s = 0.0;
+          for (int k = a + lane; k < b; k += 32) s = __dadd_rn(s, __dmul_rn(tv[k], __ldg(&x[ti[k]])));
+          s = warp_sum(s);
+          if (lane == 0) {
+            if (init != nullptr) s += init_sign * init[row];
+            spmv_epilogue<POST>(s, row, y, d, v, dot_acc);
+          }
+        }
+      } else if (cw == 0) {
+        // chunk of one very long row: consumer warp 0 alone, carry across chunks in lane 0
+        double s = 0.0;
+        for (int k = lane; k < nnz; k += 32) s = __dadd_rn(s, __dmul_rn(tv[k], __ldg(&x[ti[k]])));
+        s = warp_sum(s);
+        if (lane == 0) {
+          if (type == TILE_LONG_FIRST || type == TILE_LONG_ONLY)
+            carry = (init != nullptr) ? init_sign * init[row0] : 0.0;
+          carry += s;
+          if (type == TILE_LONG_LAST || type == TILE_LONG_ONLY)
+            spmv_epilogue<POST>(carry, row0, y, d, v, dot_acc);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[st]);
+    }
+  }
+
+  if (POST == B200_POST_FMA_DOT) {
+    double acc[1] = {dot_acc};
+    block_sum<1>(acc, s_red);
+    if (grid_finish<1>(acc, partials, counter, 0u, s_red)) {
+      if (tid == 0) {
+        *dot_out = acc[0];
+        if (hook == B200_HOOK_CG_ALPHA) {
+          B200CgCtl *c = reinterpret_cast<B200CgCtl *>(hook_arg);
+          c->pGp = acc[0];
+          c->alpha = c->ztr / acc[0];
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ host side
 static int lanes_log2_for(int max_row_nnz) {
   if (max_row_nnz <= 16) return 0;
@@ -278,11 +495,19 @@ extern "C" B200Spmv *b200_spmv_create(int nrows, int ncols, const int *h_rowptr,
 
   // tile size: full tiles for big matrices, smaller ones so that small matrices
   // still spread over all SMs
-  long long want = nnz / (4LL * nsm);
-  int tile_nnz = 256;
-  while (tile_nnz < SPMV_TILE_NNZ && tile_nnz < want) tile_nnz <<= 1;
+  {
+    const char *e = getenv("SCS_B200_SPMV");
+    M->version = e ? atoi(e) : SPMV_DEFAULT_VERSION;
+    if (M->version != 1 && M->version != 2) M->version = SPMV_DEFAULT_VERSION;
+  }
+  const int max_tile = M->version == 2 ? SPMV2_TILE_NNZ : SPMV_TILE_NNZ;
+  const int ctas_per_sm = M->version == 2 ? SPMV2_CTAS_PER_SM : SPMV_CTAS_PER_SM;
+  long long want = nnz / (2LL * ctas_per_sm * nsm);
+  int tile_nnz = 256 < max_tile ? 256 : max_tile;
+  while (tile_nnz < max_tile && tile_nnz < want) tile_nnz <<= 1;
+  if (tile_nnz > max_tile) tile_nnz = max_tile;
   M->tile_nnz = tile_nnz;
-  const int tile_rows = SPMV_TILE_ROWS;
+  const int tile_rows = M->version == 2 ? SPMV2_TILE_ROWS : SPMV_TILE_ROWS;
 
   std::vector<int4> tiles;
   tiles.reserve((size_t)(nnz / tile_nnz + nrows / tile_rows + 16));
@@ -331,7 +556,7 @@ extern "C" B200Spmv *b200_spmv_create(int nrows, int ncols, const int *h_rowptr,
     r = r1;
   }
   M->ntiles = (int)tiles.size();
-  int grid = 2 * nsm;
+  int grid = ctas_per_sm * nsm;
   if (grid > M->ntiles) grid = M->ntiles;
   if (grid < 1) grid = 1;
   M->grid = grid;
@@ -356,7 +581,7 @@ extern "C" B200Spmv *b200_spmv_create(int nrows, int ncols, const int *h_rowptr,
   }
 
   const size_t pad_nnz = (size_t)((nnz + 3) & ~3LL) + 8;
-  M->d_rowptr = (int *)b200_malloc((size_t)(nrows + 1) * 4);
+  M->d_rowptr = (int *)b200_malloc((size_t)(nrows + 1 + 8) * 4);
   M->d_colidx = (int *)b200_malloc(pad_nnz * 4);
   M->d_vals = (double *)b200_malloc(pad_nnz * 8);
   M->d_tiles = (int4 *)b200_malloc((size_t)(M->ntiles > 0 ? M->ntiles : 1) * sizeof(int4));
@@ -369,6 +594,7 @@ extern "C" B200Spmv *b200_spmv_create(int nrows, int ncols, const int *h_rowptr,
     return nullptr;
   }
   int rc = 0;
+  rc |= b200_memset0(M->d_rowptr, (size_t)(nrows + 1 + 8) * 4);
   rc |= b200_memset0(M->d_colidx, pad_nnz * 4);
   rc |= b200_memset0(M->d_vals, pad_nnz * 8);
   rc |= b200_memset0(M->d_counter, 64);
@@ -394,6 +620,14 @@ extern "C" B200Spmv *b200_spmv_create(int nrows, int ncols, const int *h_rowptr,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spmv_smem_bytes());
     cudaFuncSetAttribute(spmv_csr_stream_kernel<B200_POST_FMA>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spmv_smem_bytes());
+    cudaFuncSetAttribute(spmv_ws_kernel<B200_POST_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)spmv2_smem_bytes());
+    cudaFuncSetAttribute(spmv_ws_kernel<B200_POST_DIV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)spmv2_smem_bytes());
+    cudaFuncSetAttribute(spmv_ws_kernel<B200_POST_FMA_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)spmv2_smem_bytes());
+    cudaFuncSetAttribute(spmv_ws_kernel<B200_POST_FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)spmv2_smem_bytes());
     attr_done = true;
   }
   return M;
@@ -425,13 +659,17 @@ extern "C" double b200_spmv_alg_bytes(const B200Spmv *M, int extra_row_vectors) 
 extern "C" int b200_spmv(const B200Spmv *M, const B200SpmvArgs *a) {
   if (M->nrows == 0) return 0;
   cudaStream_t st = (cudaStream_t)b200_stream();
-  const size_t smem = spmv_smem_bytes();
-  dim3 grid(M->grid), block(SPMV_THREADS);
-#define LAUNCH(POSTV)                                                                          \
-  spmv_csr_stream_kernel<POSTV><<<grid, block, smem, st>>>(                                    \
-      M->d_rowptr, M->d_colidx, M->d_vals, M->d_tiles, M->d_cta_tile_begin, a->d_x, a->d_y,    \
+  const size_t smem = M->version == 2 ? spmv2_smem_bytes() : spmv_smem_bytes();
+  dim3 grid(M->grid), block(M->version == 2 ? SPMV2_THREADS : SPMV_THREADS);
+#define ARGS                                                                                   \
+  M->d_rowptr, M->d_colidx, M->d_vals, M->d_tiles, M->d_cta_tile_begin, a->d_x, a->d_y,        \
       a->d_init, a->init_sign, a->d_d, a->d_v, a->d_dot, a->hook, a->d_hook_arg, a->d_skip,    \
-      M->d_partials, M->d_counter)
+      M->d_partials, M->d_counter
+#define LAUNCH(POSTV)                                                                          \
+  do {                                                                                         \
+    if (M->version == 2) spmv_ws_kernel<POSTV><<<grid, block, smem, st>>>(ARGS);               \
+    else spmv_csr_stream_kernel<POSTV><<<grid, block, smem, st>>>(ARGS);                       \
+  } while (0)
   switch (a->post) {
     case B200_POST_NONE: LAUNCH(B200_POST_NONE); break;
     case B200_POST_DIV: LAUNCH(B200_POST_DIV); break;
@@ -440,6 +678,7 @@ extern "C" int b200_spmv(const B200Spmv *M, const B200SpmvArgs *a) {
     default: return -1;
   }
 #undef LAUNCH
+#undef ARGS
   b200_count_launch(1);
   CUDA_OK(cudaGetLastError());
   return 0;

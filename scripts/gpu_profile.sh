@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 TAG=${TAG:-r01}
 python scripts/prof_spmv.py 2>&1 | tail -4
 # full section set for the SpMV kernels (skip warm-up launches)
-ncu --set full --clock-control none --import-source on -k regex:spmv_csr_stream -s 8 -c 4 \
+ncu --set full --clock-control none --import-source on -k regex:spmv_ -s 8 -c 4 \
     -o gpurun_out/spmv_${TAG} -f python scripts/prof_spmv.py > gpurun_out/ncu_spmv_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_cg_ -s 4 -c 4 \
     -o gpurun_out/cgvec_${TAG} -f python scripts/prof_spmv.py > gpurun_out/ncu_cgvec_${TAG}.log 2>&1

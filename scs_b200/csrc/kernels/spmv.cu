@@ -427,6 +427,42 @@ spmv_ws_kernel(const int *__restrict__ rowptr, const int *__restrict__ colidx,
           }
           spmv_epilogue_pre<POST>(s, row, y, dv, ev, dot_acc);
         }
+      } else if (type == TILE_NORMAL && lg <= 2) {
+        // Few, medium rows (e.g. the 10-entry rows of A'): L = 2 or 4 lanes share a row so that all
+        // consumer threads gather. Lane l of the group loads entries [base + l*CH, base + (l+1)*CH);
+        // the group leader then adds the products IN STORAGE ORDER (shuffles), so the result is
+        // still bit-identical to the sequential CPU loop.
+        const int L = 1 << lg;
+        const int lig = lane & (L - 1);
+        const unsigned gmask = ((L == 2) ? 0x3u : 0xfu) << (lane & ~(L - 1));
+        const int gsrc = lane & ~(L - 1);
+        const int gid = (cw * 32 + lane) >> lg, ngroups = (SPMV2_NCW * 32) >> lg;
+        for (int r = gid; r < nrows; r += ngroups) {
+          const int row = row0 + r;
+          const int a = rp[r] - k0, b = rp[r + 1] - k0;
+          const double dv = (POST != B200_POST_NONE) ? d[row] : 0.0;
+          const double ev = (POST == B200_POST_FMA_DOT || POST == B200_POST_FMA) ? v[row] : 0.0;
+          double s = (init != nullptr) ? init_sign * init[row] : 0.0;
+          for (int base = a; base < b; base += L * SPMV2_CHUNK) {
+            const int k = base + lig * SPMV2_CHUNK;
+            int c[SPMV2_CHUNK];
+            double pr[SPMV2_CHUNK];
+#pragma unroll
+            for (int u = 0; u < SPMV2_CHUNK; ++u) c[u] = (k + u < b) ? ti[k + u] : -1;
+#pragma unroll
+            for (int u = 0; u < SPMV2_CHUNK; ++u) pr[u] = (c[u] >= 0) ? gather_ld(&x[c[u]]) : 0.0;
+#pragma unroll
+            for (int u = 0; u < SPMV2_CHUNK; ++u) pr[u] = (c[u] >= 0) ? __dmul_rn(tv[k + u], pr[u]) : 0.0;
+            for (int l = 0; l < L; ++l) {
+#pragma unroll
+              for (int u = 0; u < SPMV2_CHUNK; ++u) {
+                const double val = __shfl_sync(gmask, pr[u], gsrc + l);
+                if (base + l * SPMV2_CHUNK + u < b) s = __dadd_rn(s, val);
+              }
+            }
+          }
+          if (lig == 0) spmv_epilogue_pre<POST>(s, row, y, dv, ev, dot_acc);
+        }
       } else if (type == TILE_NORMAL) {
         // longer rows: one warp per row, lanes stride the entries, fixed shuffle tree
         for (int r = cw; r < nrows; r += SPMV2_NCW) {
@@ -547,7 +583,22 @@ extern "C" B200Spmv *b200_spmv_create(int nrows, int ncols, const int *h_rowptr,
     }
     int4 t;
     t.x = r;
-    t.y = (r1 - r) | (TILE_NORMAL << 28) | (lanes_log2_for(mx) << 24);
+    int lgv = lanes_log2_for(mx);
+    if (M->version == 2) {
+      // v2: lg 0/1/2 = 1/2/4 lanes per row with ORDERED combine (bit-exact), 5 = warp per row (tree)
+      const int nr = r1 - r, cons = SPMV2_NCW * 32;
+      // measured on C2 (profiles/README.md): sharing a 10-entry row between 2 lanes costs 7 %
+      // (65.1 vs 60.6 us), so the ordered multi-lane mode is off unless asked for
+      lgv = 0;
+      if (mx > 64) lgv = 5;
+#ifdef SPMV2_ORDERED_LANES
+      else if (nr * 4 <= cons) lgv = 2;
+      else if (nr * 2 <= cons) lgv = 1;
+#else
+      (void)nr; (void)cons;
+#endif
+    }
+    t.y = (r1 - r) | (TILE_NORMAL << 28) | (lgv << 24);
     t.z = k0;
     t.w = cnt;
     tiles.push_back(t);

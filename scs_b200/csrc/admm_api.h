@@ -75,6 +75,7 @@ int b200_vec_scale_by(long long len, double *d_a, const double *d_d, double f);
  * bnd[1..nbnd) = sizes of the cones sharing one D value. d_D (m), d_E (n) are outputs. */
 int b200_equilibrate_dev(B200Spmv *A_rows, B200Spmv *A_cols, const int *bnd, int nbnd, double *d_D,
                          double *d_E);
+int b200_rescale_dev(B200Spmv *M, const double *d_rowscale, const double *d_colscale, int row_is_d);
 
 /* ---------------------------------------------------------------- cones (kernels/cones.cu) */
 typedef struct B200Cones B200Cones;

@@ -265,6 +265,28 @@ void scs_free_lin_sys_work(ScsLinSysWork *w) {
   free(w);
 }
 
+/* Row-sharded setup: D, E of the FULL matrix are computed on every rank from temporary full
+ * copies (both orientations) on its GPU; the resident local blocks are then scaled once. */
+int b200_linsys_full_equilibrate(const ScsMatrix *A, const int *bnd, int nbnd, double *d_D, double *d_E) {
+  int *Tp = NULL, *Ti = NULL, rc = -1;
+  double *Tx = NULL;
+  B200Spmv *At = b200_spmv_create(A->n, A->m, A->p, A->i, A->x);
+  B200Spmv *Ar = NULL;
+  if (At && transpose_csc(A->m, A->n, A->p, A->i, A->x, &Tp, &Ti, &Tx) == 0) {
+    Ar = b200_spmv_create(A->m, A->n, Tp, Ti, Tx);
+    if (Ar) rc = b200_equilibrate_dev(Ar, At, bnd, nbnd, d_D, d_E);
+  }
+  free(Tp); free(Ti); free(Tx);
+  b200_spmv_destroy(Ar);
+  b200_spmv_destroy(At);
+  return rc;
+}
+int b200_linsys_scale_local(ScsLinSysWork *w, const double *d_D, const double *d_E) {
+  if (b200_rescale_dev(w->A, d_D + w->row0, d_E, 1) != 0) return -1;   /* rows of A_g */
+  if (b200_rescale_dev(w->At, d_E, d_D + w->row0, 0) != 0) return -1;  /* columns of A_g */
+  return 0;
+}
+
 /* device-pointer solve used by the ADMM driver; d_tol optional device scalar */
 int b200_linsys_solve_dev(ScsLinSysWork *w, double *d_b, const double *d_s, double tol,
                           const double *d_tol) {

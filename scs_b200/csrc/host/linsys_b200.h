@@ -5,6 +5,7 @@
 #define LINSYS_B200_H
 #include "../../../include/scs_b200.h"
 #include "../dev_api.h"
+#include "../admm_api.h"
 
 struct SCS_LIN_SYS_WORK {
   int n, m;
@@ -29,6 +30,8 @@ struct SCS_LIN_SYS_WORK {
 int b200_linsys_solve_dev(ScsLinSysWork *w, double *d_b, const double *d_s, double tol,
                           const double *d_tol);
 int b200_linsys_update_diag_r_dev(ScsLinSysWork *w, const double *d_diag_r);
+int b200_linsys_full_equilibrate(const ScsMatrix *A, const int *bnd, int nbnd, double *d_D, double *d_E);
+int b200_linsys_scale_local(ScsLinSysWork *w, const double *d_D, const double *d_E);
 /* contiguous row blocks balanced by nonzeros; offsets[nranks+1] (also exported for the tests) */
 void b200_row_partition(int m, int n, const int *Ap, const int *Ai, int nranks, int *offsets);
 

@@ -352,7 +352,7 @@ ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {
   /* Equilibrate on the device when possible (P = 0, single GPU): the user's A is uploaded as
    * is and both resident orientations are rescaled in place (kernels/equil.cu), so no host
    * copy of A is needed at all. Otherwise (P != 0 or row-sharded) equilibrate a host copy. */
-  dev_equil = stgs->normalize && !d->P && b200_comm_nranks() == 1 && !getenv("SCS_B200_HOST_EQUIL");
+  dev_equil = stgs->normalize && !d->P && !getenv("SCS_B200_HOST_EQUIL");
   w->d->A = dev_equil ? SCS_NULL : copy_matrix(d->A);
   w->d->P = d->P ? copy_matrix(d->P) : SCS_NULL;
   w->d->b = (double *)dup_mem(d->b, (size_t)m * 8);
@@ -444,11 +444,19 @@ ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {
   if (i != 0) goto fail;
   if (dev_equil) {
     /* upload the raw A (both orientations), equilibrate in place on the device */
+    if (b200_comm_nranks() > 1) {
+      /* row-sharded: D, E from temporary full copies, then scale the resident row block once */
+      if (b200_linsys_full_equilibrate(d->A, w->cone_boundaries, w->cone_boundaries_len, w->d_D, w->d_E) != 0)
+        goto fail;
+    }
     w->p = scs_init_lin_sys_work(d->A, SCS_NULL, w->h_diag_r);
     if (!w->p) { printf("ERROR: init_lin_sys_work failure\n"); goto fail; }
-    if (b200_equilibrate_dev(w->p->A, w->p->At, w->cone_boundaries, w->cone_boundaries_len, w->d_D,
-                             w->d_E) != 0)
+    if (b200_comm_nranks() > 1) {
+      if (b200_linsys_scale_local(w->p, w->d_D, w->d_E) != 0) goto fail;
+    } else if (b200_equilibrate_dev(w->p->A, w->p->At, w->cone_boundaries, w->cone_boundaries_len,
+                                    w->d_D, w->d_E) != 0) {
       goto fail;
+    }
     if (b200_linsys_update_diag_r_dev(w->p, w->p->d_diag_r) != 0) goto fail; /* preconditioner of D A E */
     if (b200_d2h(w->D, w->d_D, (size_t)m * 8) != 0 || b200_d2h(w->E, w->d_E, (size_t)n * 8) != 0 ||
         b200_sync() != 0)

@@ -137,3 +137,18 @@ out:
   b200_free(d_off);
   return rc;
 }
+
+// vals[k] *= D[row] * E[col] once, with the accumulated D, E (row-sharded path: the local blocks
+// of A are scaled after D, E were computed from the full matrix).
+extern "C" int b200_rescale_dev(B200Spmv *M, const double *d_rowscale, const double *d_colscale,
+                                int row_is_d) {
+  cudaStream_t st = (cudaStream_t)b200_stream();
+  const int nr = b200_spmv_nrows(M);
+  if (nr <= 0) return 0;
+  k_eq_rescale<<<eq_grid(nr), 256, 0, st>>>(nr, b200_spmv_rowptr(M), b200_spmv_colidx(M),
+                                            const_cast<double *>(b200_spmv_vals(M)), d_rowscale,
+                                            d_colscale, row_is_d);
+  b200_count_launch(1);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}

@@ -102,6 +102,7 @@ typedef struct {
   int nranks, row0, mloc;
   const int *offsets;  /* host: row block boundaries, nranks+1 */
   double *d_red;       /* n: partial A_g' z before the all-reduce */
+  int use_p2p;         /* 1: fused peer-memory reduction instead of the NCCL all-reduce */
 } B200Cg;
 
 /* M_j = 1 / (R_x,j + P_jj + sum_k A_kj^2 / R_y,k)   (private.c:50-82) */
@@ -120,6 +121,13 @@ int b200_comm_rank(void);
 int b200_comm_nranks(void);
 int b200_allreduce_sum(double *d_buf, size_t count);
 int b200_allgatherv(double *d_buf, const int *offsets);
+/* peer-memory (CUDA IPC over NVLink) exchange buffers for the fused CG reduction */
+int b200_p2p_setup(int n);
+int b200_p2p_ok(int n);
+int b200_p2p_stride(void);
+double *b200_p2p_base(int r);
+unsigned long long *b200_p2p_flags(int r);
+unsigned long long b200_p2p_next_seq(void);
 
 /* ------------------------------------------------------------ vector ops - */
 /* out = |a|_inf etc. are produced into device scalars; see admm.cu */

@@ -230,6 +230,8 @@ ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
   w->cg.d_rx = w->d_diag_r;
   w->cg.d_ry = w->d_diag_r + n;
   w->cg.nranks = w->nranks; w->cg.row0 = w->row0; w->cg.mloc = w->mloc; w->cg.offsets = w->offsets;
+  /* fused peer-memory reduction (NVLink, CUDA IPC) when every rank could map every peer */
+  w->cg.use_p2p = (w->nranks > 1 && b200_p2p_setup(n) == 0 && b200_p2p_ok(n)) ? 1 : 0;
   if (b200_h2d(w->d_diag_r, diag_r, ((size_t)n + m) * 8) != 0) goto fail;
   if (b200_cg_set_preconditioner(&w->cg, w->d_Pdiag) != 0) goto fail;
   if (b200_sync() != 0) goto fail;

@@ -263,6 +263,62 @@ k_cg_finish_mv(int n, double *__restrict__ y, const double *__restrict__ red, in
     }
   }
 }
+// Fused "all-reduce + finish" over NVLink peer memory: every rank has written its partial
+// A_g' z into its own exchange buffer (slot seq & 1); this kernel (i) publishes "my partial of
+// step seq is ready" into every peer's flag line, (ii) waits until every peer has published the
+// same step, (iii) reads all partials -- the remote ones straight through the mapped peer
+// pointers -- adds them IN RANK ORDER (so every rank gets the same bits), applies R_x p (+ P p)
+// and reduces p'Gp. No NCCL call, no separate finish pass.
+struct P2pView {
+  int nranks, rank, stride;
+  const double *base[8];
+  unsigned long long *flags[8];
+};
+__global__ void __launch_bounds__(VEC_THREADS)
+k_cg_finish_p2p(int n, double *__restrict__ y, P2pView pv, unsigned long long seq, int y_has_px,
+                const double *__restrict__ rx, const double *__restrict__ x, int with_dot,
+                B200CgCtl *ctl, const int *skip, double *partials, unsigned int *counter) {
+  if (skip != nullptr && *skip) return;
+  __shared__ double s_red[64];
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      for (int r = 0; r < pv.nranks; ++r)
+        if (r != pv.rank) *((volatile unsigned long long *)(pv.flags[r] + pv.rank)) = seq;
+    }
+    volatile unsigned long long *mine = pv.flags[pv.rank];
+    const long long t0 = clock64();
+    for (int r = 0; r < pv.nranks; ++r) {
+      if (r == pv.rank) continue;
+      while (mine[r] < seq) {
+        // never hang the GPU: after ~10 s (2e10 cycles) flag an error and go on (the host aborts the solve)
+        if (clock64() - t0 > 20000000000LL) { ctl->pad[0] = 1; break; }
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const size_t slot = (size_t)(seq & 1ull) * pv.stride;
+  double acc[1] = {0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double sum = 0.0;
+    for (int r = 0; r < pv.nranks; ++r) sum += __ldcg(pv.base[r] + slot + i);
+    const double base = y_has_px ? y[i] + sum : sum;
+    const double xi = x[i];
+    const double out = fma(rx[i], xi, base);
+    y[i] = out;
+    acc[0] = fma(xi, out, acc[0]);
+  }
+  if (!with_dot) return;
+  block_sum<1>(acc, s_red);
+  if (grid_finish<1>(acc, partials, counter, 0u, s_red)) {
+    if (threadIdx.x == 0) {
+      ctl->pGp = acc[0];
+      ctl->alpha = ctl->ztr / acc[0];
+    }
+  }
+}
+
 __global__ void k_add_if_not(int n, double *__restrict__ a, const double *__restrict__ b, const int *skip) {
   if (skip != nullptr && *skip) return;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a[i] += b[i];
@@ -322,15 +378,35 @@ static int mat_vec_sharded(B200Cg *cg, const double *d_x, double *d_y, int with_
   a.d_d = cg->d_ry + cg->row0; a.d_skip = d_skip;
   if (b200_spmv(cg->A, &a) != 0) return -1;
   // local partial  red = A_g' tmp_g ; sum over ranks
-  a.d_x = cg->d_tmp + cg->row0; a.d_y = cg->d_red; a.post = B200_POST_NONE; a.d_d = nullptr;
+  unsigned long long seq = 0;
+  double *red = cg->d_red;
+  if (cg->use_p2p) {
+    seq = b200_p2p_next_seq();
+    red = b200_p2p_base(b200_comm_rank()) + (size_t)(seq & 1ull) * b200_p2p_stride();
+  }
+  a.d_x = cg->d_tmp + cg->row0; a.d_y = red; a.post = B200_POST_NONE; a.d_d = nullptr;
   if (b200_spmv(cg->At, &a) != 0) return -1;
-  if (b200_allreduce_sum(cg->d_red, (size_t)cg->n) != 0) return -1;
+  if (!cg->use_p2p && b200_allreduce_sum(cg->d_red, (size_t)cg->n) != 0) return -1;
   if (cg->P) {  // P is replicated
     a.d_x = d_x; a.d_y = d_y;
     if (b200_spmv(cg->P, &a) != 0) return -1;
   }
   int g = (cg->n + VEC_THREADS * 4 - 1) / (VEC_THREADS * 4);
   if (g > 2 * b200_num_sms()) g = 2 * b200_num_sms();
+  if (cg->use_p2p) {
+    P2pView pv;
+    pv.nranks = cg->nranks; pv.rank = b200_comm_rank(); pv.stride = b200_p2p_stride();
+    for (int r = 0; r < 8; ++r) {
+      pv.base[r] = r < cg->nranks ? b200_p2p_base(r) : nullptr;
+      pv.flags[r] = r < cg->nranks ? b200_p2p_flags(r) : nullptr;
+    }
+    if (g > b200_num_sms()) g = b200_num_sms();  // all blocks spin on the flags: keep them co-resident
+    k_cg_finish_p2p<<<g, VEC_THREADS, 0, st>>>(cg->n, d_y, pv, seq, cg->P != nullptr, cg->d_rx, d_x,
+                                               with_dot, cg->d_ctl, d_skip, cg->d_partials,
+                                               cg->d_counter);
+    b200_count_launch(1);
+    return 0;
+  }
   k_cg_finish_mv<<<g, VEC_THREADS, 0, st>>>(cg->n, d_y, cg->d_red, cg->P != nullptr, cg->d_rx, d_x,
                                             with_dot, cg->d_ctl, d_skip, cg->d_partials, cg->d_counter);
   b200_count_launch(1);
@@ -432,6 +508,10 @@ extern "C" int b200_cg_solve(B200Cg *cg, double *d_b, const double *d_s, double 
     enq += batch;
     CUDA_OK(cudaMemcpyAsync(cg->h_ctl, cg->d_ctl, sizeof(B200CgCtl), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
+    if (cg->h_ctl->pad[0]) {
+      b200_set_error("peer-memory wait timed out in k_cg_finish_p2p", cudaErrorUnknown, __FILE__, __LINE__);
+      return -1;
+    }
     if (cg->h_ctl->done) break;
     if (enq >= (long long)max_its + 1) break;  // safety; device sets done at max_its
     batch = batch < 16 ? 16 : (batch < 64 ? batch * 2 : 64);

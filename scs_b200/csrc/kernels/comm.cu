@@ -11,7 +11,9 @@
 #include "../dev_api.h"
 #include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <vector>
 
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
@@ -112,4 +114,80 @@ extern "C" int b200_allgatherv(double *d_buf, const int *offsets) {
   }
   NCCL_OK(N.GroupEnd());
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Peer-memory exchange buffers (NVLink P2P through CUDA IPC) for the fused "sum the partial
+// A_g' z over the ranks + R_x p + p'Gp" kernel of the row-sharded CG (kernels/cg.cu). Each rank
+// owns ONE allocation: red[2][n] doubles (double-buffered partials) followed by a flag line
+// per rank; every rank maps the allocation of every other rank. The handles travel in one
+// NCCL all-gather at setup; after that the CG inner loop does not call NCCL at all.
+#define P2P_MAX_RANKS 8
+typedef struct {
+  int ok, n;
+  double *base[P2P_MAX_RANKS];               // base[r]: rank r's allocation as mapped in THIS process
+  unsigned long long *flags[P2P_MAX_RANKS];  // flags[r] = (unsigned long long*)(base[r] + 2 n)
+} B200P2p;
+static B200P2p g_p2p;
+static ncclResult_t (*N_AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+
+static unsigned long long g_p2p_seq = 0;
+extern "C" int b200_p2p_ok(int n) { return g_p2p.ok && g_p2p.n >= n; }
+extern "C" int b200_p2p_stride(void) { return g_p2p.n; }
+extern "C" double *b200_p2p_base(int r) { return g_p2p.base[r]; }
+extern "C" unsigned long long *b200_p2p_flags(int r) { return g_p2p.flags[r]; }
+extern "C" unsigned long long b200_p2p_next_seq(void) { return ++g_p2p_seq; }
+
+extern "C" int b200_p2p_setup(int n) {
+  if (g_nranks <= 1 || g_nranks > P2P_MAX_RANKS) return -1;
+  if (g_p2p.ok && g_p2p.n >= n) return 0;
+  if (g_p2p.ok) return -1;  // one size per process (all workspaces of a process share n in practice)
+  const char *e = getenv("SCS_B200_P2P");
+  if (e && atoi(e) == 0) return -1;
+  if (!N_AllGather) *(void **)(&N_AllGather) = dlsym(N.h, "ncclAllGather");
+  if (!N_AllGather) return -1;
+  cudaStream_t st = (cudaStream_t)b200_stream();
+  const size_t bytes = ((size_t)2 * n + 64) * 8;
+  double *mine = (double *)b200_malloc(bytes);
+  if (!mine) return -1;
+  if (b200_memset0(mine, bytes) != 0) return -1;
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, mine) != cudaSuccess) { cudaGetLastError(); b200_free(mine); return -1; }
+  // all-gather the 64-byte handles through NCCL (device buffers)
+  char *d_all = (char *)b200_malloc((size_t)g_nranks * sizeof(h));
+  std::vector<cudaIpcMemHandle_t> all(g_nranks);
+  int rc = -1;
+  if (d_all && cudaMemcpyAsync(d_all + (size_t)g_rank * sizeof(h), &h, sizeof(h), cudaMemcpyHostToDevice, st) == cudaSuccess &&
+      N_AllGather(d_all + (size_t)g_rank * sizeof(h), d_all, sizeof(h), /*ncclChar*/ 0, g_comm, st) == 0 &&
+      cudaMemcpyAsync(all.data(), d_all, (size_t)g_nranks * sizeof(h), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+      cudaStreamSynchronize(st) == cudaSuccess) {
+    rc = 0;
+    for (int r = 0; r < g_nranks && rc == 0; ++r) {
+      void *p = mine;
+      if (r != g_rank &&
+          cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        rc = -1;
+        break;
+      }
+      g_p2p.base[r] = (double *)p;
+      g_p2p.flags[r] = (unsigned long long *)((double *)p + (size_t)2 * n);
+    }
+  }
+  b200_free(d_all);
+  // every rank must agree that the mapping worked (otherwise all fall back to NCCL)
+  {
+    double *d_flag = (double *)b200_malloc(8);
+    double hv = (rc == 0) ? 0.0 : 1.0, out = 1.0;
+    if (d_flag && cudaMemcpyAsync(d_flag, &hv, 8, cudaMemcpyHostToDevice, st) == cudaSuccess &&
+        b200_allreduce_sum(d_flag, 1) == 0 &&
+        cudaMemcpyAsync(&out, d_flag, 8, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+        cudaStreamSynchronize(st) == cudaSuccess && out == 0.0) {
+      g_p2p.ok = 1;
+      g_p2p.n = n;
+    }
+    b200_free(d_flag);
+  }
+  if (!g_p2p.ok) fprintf(stderr, "scs_b200: peer-memory (CUDA IPC) mapping unavailable, using NCCL all-reduce\n");
+  return g_p2p.ok ? 0 : -1;
 }

@@ -52,7 +52,13 @@ const int *b200_spmv_rowptr(const B200Spmv *M);    /* device */
 double b200_spmv_alg_bytes(const B200Spmv *M, int extra_row_vectors);
 
 enum { B200_POST_NONE = 0, B200_POST_DIV = 1, B200_POST_FMA_DOT = 2, B200_POST_FMA = 3 };
-enum { B200_HOOK_NONE = 0, B200_HOOK_CG_ALPHA = 1 };
+enum { B200_HOOK_NONE = 0, B200_HOOK_CG_ALPHA = 1, B200_HOOK_P2P_SIGNAL = 2 };
+/* B200_HOOK_P2P_SIGNAL: when the LAST block of the launch has stored its rows, it publishes
+ * hook_val into slot `rank` of every peer's flag line (d_hook_arg -> B200P2pSignal). */
+typedef struct {
+  int nranks, rank;
+  unsigned long long *flags[8]; /* flags[r]: flag line of rank r as mapped in this process */
+} B200P2pSignal;
 
 typedef struct {
   const double *d_x;     /* gather vector, length ncols */
@@ -64,7 +70,8 @@ typedef struct {
   const double *d_v;
   double *d_dot;         /* B200_POST_FMA_DOT: receives sum_r v[r]*y[r] */
   int hook;              /* B200_HOOK_*: run by the last block after the dot is final */
-  void *d_hook_arg;      /* B200CgCtl* for B200_HOOK_CG_ALPHA */
+  void *d_hook_arg;      /* B200CgCtl* for B200_HOOK_CG_ALPHA, B200P2pSignal* for B200_HOOK_P2P_SIGNAL */
+  unsigned long long hook_val;
   const int *d_skip;     /* optional: kernel returns at once if *d_skip != 0 */
 } B200SpmvArgs;
 
@@ -103,6 +110,7 @@ typedef struct {
   const int *offsets;  /* host: row block boundaries, nranks+1 */
   double *d_red;       /* n: partial A_g' z before the all-reduce */
   int use_p2p;         /* 1: fused peer-memory reduction instead of the NCCL all-reduce */
+  B200P2pSignal *d_p2p_sig; /* device copy of the peer flag table */
 } B200Cg;
 
 /* M_j = 1 / (R_x,j + P_jj + sum_k A_kj^2 / R_y,k)   (private.c:50-82) */

@@ -232,6 +232,15 @@ ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
   w->cg.nranks = w->nranks; w->cg.row0 = w->row0; w->cg.mloc = w->mloc; w->cg.offsets = w->offsets;
   /* fused peer-memory reduction (NVLink, CUDA IPC) when every rank could map every peer */
   w->cg.use_p2p = (w->nranks > 1 && b200_p2p_setup(n) == 0 && b200_p2p_ok(n)) ? 1 : 0;
+  if (w->cg.use_p2p) {
+    B200P2pSignal sig;
+    int r;
+    memset(&sig, 0, sizeof(sig));
+    sig.nranks = w->nranks; sig.rank = w->rank;
+    for (r = 0; r < w->nranks && r < 8; ++r) sig.flags[r] = b200_p2p_flags(r);
+    w->cg.d_p2p_sig = (B200P2pSignal *)b200_malloc(sizeof(sig));
+    if (!w->cg.d_p2p_sig || b200_h2d(w->cg.d_p2p_sig, &sig, sizeof(sig)) != 0) goto fail;
+  }
   if (b200_h2d(w->d_diag_r, diag_r, ((size_t)n + m) * 8) != 0) goto fail;
   if (b200_cg_set_preconditioner(&w->cg, w->d_Pdiag) != 0) goto fail;
   if (b200_sync() != 0) goto fail;
@@ -262,6 +271,7 @@ void scs_free_lin_sys_work(ScsLinSysWork *w) {
   b200_free(w->cg.d_partials);
   b200_free(w->cg.d_counter);
   b200_free(w->cg.d_red);
+  b200_free(w->cg.d_p2p_sig);
   b200_host_free(w->cg.h_ctl);
   free(w->offsets);
   free(w);

@@ -275,13 +275,14 @@ struct P2pView {
   unsigned long long *flags[8];
 };
 __global__ void __launch_bounds__(VEC_THREADS)
-k_cg_finish_p2p(int n, double *__restrict__ y, P2pView pv, unsigned long long seq, int y_has_px,
-                const double *__restrict__ rx, const double *__restrict__ x, int with_dot,
-                B200CgCtl *ctl, const int *skip, double *partials, unsigned int *counter) {
+k_cg_finish_p2p(int n, double *__restrict__ y, P2pView pv, unsigned long long seq, int do_signal,
+                int y_has_px, const double *__restrict__ rx, const double *__restrict__ x,
+                int with_dot, B200CgCtl *ctl, const int *skip, double *partials,
+                unsigned int *counter) {
   if (skip != nullptr && *skip) return;
   __shared__ double s_red[64];
   if (threadIdx.x == 0) {
-    if (blockIdx.x == 0) {
+    if (do_signal && blockIdx.x == 0) {  // only when the producing SpMV did not signal itself
       __threadfence_system();
       for (int r = 0; r < pv.nranks; ++r)
         if (r != pv.rank) *((volatile unsigned long long *)(pv.flags[r] + pv.rank)) = seq;
@@ -300,14 +301,34 @@ k_cg_finish_p2p(int n, double *__restrict__ y, P2pView pv, unsigned long long se
   __syncthreads();
   const size_t slot = (size_t)(seq & 1ull) * pv.stride;
   double acc[1] = {0.0};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    double sum = 0.0;
-    for (int r = 0; r < pv.nranks; ++r) sum += __ldcg(pv.base[r] + slot + i);
-    const double base = y_has_px ? y[i] + sum : sum;
-    const double xi = x[i];
-    const double out = fma(rx[i], xi, base);
-    y[i] = out;
-    acc[0] = fma(xi, out, acc[0]);
+  constexpr int U = 4;  // independent remote loads in flight per thread and rank
+  const int stride = gridDim.x * blockDim.x;
+  for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += U * stride) {
+    double sum[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) sum[u] = 0.0;
+    for (int r = 0; r < pv.nranks; ++r) {  // rank order => identical bits on every rank
+      const double *src = pv.base[r] + slot;
+      double t[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * stride;
+        t[u] = (i < n) ? __ldcg(src + i) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) sum[u] += t[u];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * stride;
+      if (i < n) {
+        const double base = y_has_px ? y[i] + sum[u] : sum[u];
+        const double xi = x[i];
+        const double out = fma(rx[i], xi, base);
+        y[i] = out;
+        acc[0] = fma(xi, out, acc[0]);
+      }
+    }
   }
   if (!with_dot) return;
   block_sum<1>(acc, s_red);
@@ -385,7 +406,11 @@ static int mat_vec_sharded(B200Cg *cg, const double *d_x, double *d_y, int with_
     red = b200_p2p_base(b200_comm_rank()) + (size_t)(seq & 1ull) * b200_p2p_stride();
   }
   a.d_x = cg->d_tmp + cg->row0; a.d_y = red; a.post = B200_POST_NONE; a.d_d = nullptr;
+  if (cg->use_p2p && cg->d_p2p_sig) {  // the SpMV's last block publishes "partial ready" to the peers
+    a.hook = B200_HOOK_P2P_SIGNAL; a.d_hook_arg = cg->d_p2p_sig; a.hook_val = seq;
+  }
   if (b200_spmv(cg->At, &a) != 0) return -1;
+  a.hook = B200_HOOK_NONE; a.d_hook_arg = nullptr; a.hook_val = 0;
   if (!cg->use_p2p && b200_allreduce_sum(cg->d_red, (size_t)cg->n) != 0) return -1;
   if (cg->P) {  // P is replicated
     a.d_x = d_x; a.d_y = d_y;
@@ -401,7 +426,8 @@ static int mat_vec_sharded(B200Cg *cg, const double *d_x, double *d_y, int with_
       pv.flags[r] = r < cg->nranks ? b200_p2p_flags(r) : nullptr;
     }
     if (g > b200_num_sms()) g = b200_num_sms();  // all blocks spin on the flags: keep them co-resident
-    k_cg_finish_p2p<<<g, VEC_THREADS, 0, st>>>(cg->n, d_y, pv, seq, cg->P != nullptr, cg->d_rx, d_x,
+    k_cg_finish_p2p<<<g, VEC_THREADS, 0, st>>>(cg->n, d_y, pv, seq, cg->d_p2p_sig == nullptr,
+                                               cg->P != nullptr, cg->d_rx, d_x,
                                                with_dot, cg->d_ctl, d_skip, cg->d_partials,
                                                cg->d_counter);
     b200_count_launch(1);

@@ -150,7 +150,7 @@ spmv_csr_stream_kernel(const int *__restrict__ rowptr, const int *__restrict__ c
                        double *__restrict__ y, const double *init, double init_sign,
                        const double *__restrict__ d, const double *__restrict__ v, double *dot_out,
                        int hook, void *hook_arg, const int *skip, double *partials,
-                       unsigned int *counter) {
+                       unsigned int *counter, unsigned long long hook_val) {
   if (skip != nullptr && *((volatile const int *)skip) != 0) return;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -284,6 +284,22 @@ spmv_csr_stream_kernel(const int *__restrict__ rowptr, const int *__restrict__ c
       spmv_issue_tile(tiles[t_begin + i + SPMV_STAGES], st, s_vals, s_idx, s_bar, vals, colidx, pol);
   }
 
+  if (hook == B200_HOOK_P2P_SIGNAL) {
+    // multi-GPU: tell every peer that this rank's partial product is complete (last block only)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned tk = atomicAdd(counter, 1u);
+      if (tk == gridDim.x - 1) {
+        *counter = 0u;
+        __threadfence_system();
+        const B200P2pSignal *ps = reinterpret_cast<const B200P2pSignal *>(hook_arg);
+        for (int r = 0; r < ps->nranks; ++r)
+          if (r != ps->rank) *((volatile unsigned long long *)(ps->flags[r] + ps->rank)) = hook_val;
+      }
+    }
+  }
+
   if (POST == B200_POST_FMA_DOT) {
     double acc[1] = {dot_acc};
     block_sum<1>(acc, s_red);
@@ -343,7 +359,8 @@ spmv_ws_kernel(const int *__restrict__ rowptr, const int *__restrict__ colidx,
                const int *__restrict__ cta_tile_begin, const double *__restrict__ x,
                double *__restrict__ y, const double *init, double init_sign,
                const double *__restrict__ d, const double *__restrict__ v, double *dot_out, int hook,
-               void *hook_arg, const int *skip, double *partials, unsigned int *counter) {
+               void *hook_arg, const int *skip, double *partials, unsigned int *counter,
+               unsigned long long hook_val) {
   if (skip != nullptr && *((volatile const int *)skip) != 0) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *s_vals = reinterpret_cast<double *>(smem_raw);
@@ -491,6 +508,22 @@ spmv_ws_kernel(const int *__restrict__ rowptr, const int *__restrict__ colidx,
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[st]);
+    }
+  }
+
+  if (hook == B200_HOOK_P2P_SIGNAL) {
+    // multi-GPU: tell every peer that this rank's partial product is complete (last block only)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned tk = atomicAdd(counter, 1u);
+      if (tk == gridDim.x - 1) {
+        *counter = 0u;
+        __threadfence_system();
+        const B200P2pSignal *ps = reinterpret_cast<const B200P2pSignal *>(hook_arg);
+        for (int r = 0; r < ps->nranks; ++r)
+          if (r != ps->rank) *((volatile unsigned long long *)(ps->flags[r] + ps->rank)) = hook_val;
+      }
     }
   }
 
@@ -715,7 +748,7 @@ extern "C" int b200_spmv(const B200Spmv *M, const B200SpmvArgs *a) {
 #define ARGS                                                                                   \
   M->d_rowptr, M->d_colidx, M->d_vals, M->d_tiles, M->d_cta_tile_begin, a->d_x, a->d_y,        \
       a->d_init, a->init_sign, a->d_d, a->d_v, a->d_dot, a->hook, a->d_hook_arg, a->d_skip,    \
-      M->d_partials, M->d_counter
+      M->d_partials, M->d_counter, a->hook_val
 #define LAUNCH(POSTV)                                                                          \
   do {                                                                                         \
     if (M->version == 2) spmv_ws_kernel<POSTV><<<grid, block, smem, st>>>(ARGS);               \

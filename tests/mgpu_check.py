@@ -47,7 +47,7 @@ for name, prob in (
     ("c2_small", problems.config("C2", scale=0.02)),
 ):
     st1, info1, x1, y1, s1 = solve(lib, prob, max_iters=1)
-    st, info, x, y, s = solve(lib, prob, eps_abs=1e-6, eps_rel=1e-6, max_iters=20000)
+    st, info, x, y, s = solve(lib, prob, eps_abs=1e-5, eps_rel=1e-5, max_iters=8000)
     # every rank must hold the same answer
     t = torch.tensor([info.pobj, float(info.iter)], device="cuda", dtype=torch.float64)
     tmax, tmin = t.clone(), t.clone()
@@ -57,9 +57,9 @@ for name, prob in (
     if rank == 0:
         _, _, xr, yr, sr = solve(ref, prob, max_iters=1)
         err1 = max(np.abs(a - b).max() / max(1.0, np.abs(b).max()) for a, b in ((x1, xr), (y1, yr), (s1, sr)))
-        str_, infor, *_ = solve(ref, prob, eps_abs=1e-6, eps_rel=1e-6, max_iters=20000)
+        str_, infor, *_ = solve(ref, prob, eps_abs=1e-5, eps_rel=1e-5, max_iters=8000)
         dobj = abs(info.pobj - infor.pobj) / max(1.0, abs(infor.pobj))
-        good = same and err1 <= 1e-9 and st == str_ == 1 and dobj <= 1e-4 and abs(info.pobj - prob["opt"]) <= 1e-3 * max(1, abs(prob["opt"]))
+        good = same and err1 <= 1e-9 and st == str_ == 1 and dobj <= 1e-3 and abs(info.pobj - prob["opt"]) <= 1e-3 * max(1, abs(prob["opt"]))
         print(f"[{name}] ranks agree={same} one-iteration err vs reference={err1:.2e} status={st}/{str_} "
               f"iters={info.iter}/{infor.iter} pobj={info.pobj:.9e}/{infor.pobj:.9e} -> {'OK' if good else 'FAIL'}", flush=True)
         ok = ok and good

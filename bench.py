@@ -382,7 +382,8 @@ def main():
             "config": {"workload": f"{args.config}: {CONFIG_DESC.get(args.config, '')}", "scale": args.scale,
                        "n": n, "m": m, "nnz": nnz, "settings": "SCS defaults (AA mem 10, adaptive scale), eps=0 so "
                        "exactly K iterations run", "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: A row-sharded by nnz-balanced row "
-                       "blocks, x-space replicated, one NCCL all-reduce of the n-vector per CG iteration",
+                       "blocks, x-space replicated; per CG iteration the partial A_g'z (n doubles) of every rank is "
+                       "summed by a fused kernel reading the peers over NVLink (CUDA IPC; NCCL all-reduce fallback)",
                        "l2": "working set (A, A' = 2 x 124 MB + vectors) exceeds the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": h2d / args.steps,
                     "d2h_bytes_per_step": d2h / args.steps,

@@ -20,6 +20,20 @@ dr = np.empty(n + m + 1)
 dr[:n] = 1e-6
 dr[n:] = 10.0
 w = lib.scs_init_lin_sys_work(C.byref(hp.A), None, capi.dptr(dr))
+if os.environ.get("CHECK"):
+    # full-size parity of both operators against numpy (CSC scatter / gather in fp64)
+    x = rng.standard_normal(n)
+    yv = rng.standard_normal(m)
+    mine = np.zeros(m)
+    assert lib.scs_b200_accum_by_a(w, capi.dptr(x), capi.dptr(mine), 0) == 0
+    ref = problems.csc_matvec(A, x)
+    e1 = np.abs(mine - ref).max() / np.abs(ref).max()
+    mine = np.zeros(n)
+    assert lib.scs_b200_accum_by_atrans(w, capi.dptr(yv), capi.dptr(mine), 0) == 0
+    ref = problems.csc_rmatvec(A, yv)
+    e2 = np.abs(mine - ref).max() / np.abs(ref).max()
+    print(f"full-size parity vs numpy: A x {e1:.2e}  A'y {e2:.2e}")
+    assert e1 < 1e-12 and e2 < 1e-12
 ab = C.c_double()
 reps = int(os.environ.get("REPS", "5"))
 for op in (0, 1):

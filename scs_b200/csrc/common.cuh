@@ -12,6 +12,8 @@
 #define B200_NUM_SMS_FALLBACK 148
 #define B200_RED_THREADS 512  // threads per block of every reduction-carrying vector kernel
 #define B200_MAX_PARTIALS 2048
+// stored column indices carry flags in bits 30/31 (kernels/spmv.cu, flagged stream); every reader masks
+#define B200_COLMASK 0x3fffffff
 
 #define CUDA_OK(call)                                                        \
   do {                                                                       \

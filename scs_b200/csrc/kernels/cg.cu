@@ -45,7 +45,7 @@ __global__ void k_set_preconditioner(int n, const int *__restrict__ colptr,
     const int a = colptr[j], b = colptr[j + 1];
     for (int k = a; k < b; ++k) {
       const double v = vals[k];
-      acc += v * v / ry[rowidx[k]];
+      acc += v * v / ry[rowidx[k] & B200_COLMASK];  // top bits of stored indices are flags (spmv.cu v3)
     }
     if (pdiag != nullptr) acc += pdiag[j];
     M[j] = 1.0 / acc;
@@ -352,7 +352,7 @@ __global__ void k_precond_partial(int n, const int *__restrict__ colptr, const i
     double acc = 0.0;
     for (int k = colptr[j]; k < colptr[j + 1]; ++k) {
       const double v = vals[k];
-      acc += v * v / ry_loc[rowidx[k]];
+      acc += v * v / ry_loc[rowidx[k] & B200_COLMASK];
     }
     out[j] = acc;
   }

@@ -78,7 +78,7 @@ __global__ void k_eq_rescale(int nrows, const int *__restrict__ rowptr, const in
     const double rs = rowscale[r];
     const int a = rowptr[r], b = rowptr[r + 1];
     for (int k = a; k < b; ++k) {
-      const double cs = colscale[colidx[k]];
+      const double cs = colscale[colidx[k] & B200_COLMASK];  // flags in the top bits (spmv.cu v3)
       // reference: A->x[j] *= Dt[A->i[j]] * ei  -> always D * E in this order
       vals[k] *= row_is_d ? (rs * cs) : (cs * rs);
     }

@@ -35,7 +35,7 @@
 
 // tuning knobs (overridable with -D for sweeps; see profiles/README.md for the measurements)
 #ifndef SPMV_DEFAULT_VERSION
-#define SPMV_DEFAULT_VERSION 2  // warp-specialised pipeline (SCS_B200_SPMV=1 selects the two-phase kernel)
+#define SPMV_DEFAULT_VERSION 3  // flagged stream (SCS_B200_SPMV=2: warp-specialised row-per-lane, =1: two-phase)
 #endif
 #ifndef SPMV_THREADS
 #define SPMV_THREADS 512
@@ -75,7 +75,10 @@ struct B200Spmv {
   int tile_nnz;
   double *d_partials;
   unsigned int *d_counter;
-  int version;  // 1: two-phase block kernel, 2: warp-specialised pipeline
+  int version;  // 1: two-phase block kernel, 2: warp-specialised pipeline, 3: flagged stream
+  long long stored;  // entries held in d_colidx / d_vals (v3: nnz + one explicit zero per empty row)
+  int4 *d_wt3;       // v3 warp-tile descriptors, padded per CTA to groups of SPMV3_NCW
+  int *d_cta_begin3; // v3: first group of every CTA
 };
 
 static size_t spmv_smem_bytes() {
@@ -543,6 +546,402 @@ spmv_ws_kernel(const int *__restrict__ rowptr, const int *__restrict__ colidx,
   }
 }
 
+// ==================================================================================
+// Version 3: "flagged stream" -- nonzero-per-lane instead of row-per-lane.
+//
+// What bounds the SpMV of a uniformly random matrix is not HBM but the L1TEX pipe: every
+// nonzero costs one wavefront for its 8-byte gather (no two lanes share a 128-byte line), and
+// the row-per-thread kernels above add ~0.45 shared-memory wavefronts per nonzero on top (bank
+// conflicts of the row-strided reads of values / indices, row pointers) -- ncu: L1TEX 70-80 %.
+// v3 removes everything but the gather from that pipe:
+//   * the operator is stored as a FLAGGED stream: colidx carries "last entry of its row" in bit 31
+//     and "explicit zero, do not gather" in bit 30; every empty row owns one such zero entry, so
+//     row r is simply the r-th END flag and the kernel needs NO row pointers at all;
+//   * the stream is cut into WARP-TILES of whole rows whose 16-byte-aligned span is <= 128
+//     entries; lane l of the consumer warp owns the 4 CONSECUTIVE entries [4l, 4l+4): one
+//     LDS.128 for the indices and two conflict-free LDS.128 for the values (lanes 4..7 of every
+//     quarter-warp read their two halves in swapped order), then 4 independent gathers;
+//   * rows are recovered in registers: 4 ballots + popc give every END its row number, a
+//     sequential in-lane sum plus a warp segmented scan of the lanes' open tails (only as many
+//     shuffle steps as the longest row in the warp-tile needs) gives the row sums -- fixed order,
+//     so bit-reproducible run to run; a row inside one lane is still the CPU's sequential chain;
+//   * a CTA stages SPMV3_NCW warp-tiles (one per consumer warp) per TMA stage: value slice,
+//     index slice and the warp-tile descriptors, three bulk copies on one mbarrier; the stage is
+//     released as soon as the warp has its 48 bytes per lane in registers, before the gathers
+//     return, so the ring runs ahead of the gather latency.
+// Rows longer than SPMV3_MAXROW entries do not fit a warp-tile: such operators keep the plain
+// CSR and the v2 kernel.
+// defaults from the sweep in profiles/README.md (C2, B200): ONE CTA of 768 threads per SM (1 producer
+// + 23 consumer warps), 3 stages = 130 kB of shared memory, which leaves ~98 kB of L1 to the gathers
+#ifndef SPMV3_THREADS
+#define SPMV3_THREADS 768
+#endif
+#ifndef SPMV3_STAGES
+#define SPMV3_STAGES 3
+#endif
+#ifndef SPMV3_CTAS_PER_SM
+#define SPMV3_CTAS_PER_SM 1
+#endif
+#define SPMV3_NCW (SPMV3_THREADS / 32 - 1)
+#define SPMV3_WT 128
+#define SPMV3_CAP (SPMV3_NCW * SPMV3_WT + 8)
+#define SPMV3_MAXROW 124
+#define SPMV3_END 0x80000000u
+#define SPMV3_SKIP 0x40000000u
+
+static size_t spmv3_smem_bytes() {
+  return (size_t)SPMV3_STAGES * (SPMV3_CAP * 12 + SPMV3_NCW * 16) + 2 * SPMV3_STAGES * 8 + 64 * 8 +
+         (size_t)SPMV3_NCW * SPMV3_WT * 8;
+}
+
+template <int POST>
+__device__ __forceinline__ void spmv3_emit(double s, int row, double *__restrict__ y, const double *init,
+                                           double init_sign, const double *__restrict__ d,
+                                           const double *__restrict__ v, double &dot_acc) {
+  if (init != nullptr) s = __dadd_rn(s, init_sign * init[row]);
+  spmv_epilogue<POST>(s, row, y, d, v, dot_acc);
+}
+
+template <int POST>
+__global__ void __launch_bounds__(SPMV3_THREADS, SPMV3_CTAS_PER_SM)
+spmv_flag_kernel(const int *__restrict__ colidx, const double *__restrict__ vals,
+                 const int4 *__restrict__ wt, const int *__restrict__ cta_begin,
+                 const double *__restrict__ x, double *__restrict__ y, const double *init,
+                 double init_sign, const double *__restrict__ d, const double *__restrict__ v,
+                 double *dot_out, int hook, void *hook_arg, const int *skip, double *partials,
+                 unsigned int *counter, unsigned long long hook_val) {
+  if (skip != nullptr && *((volatile const int *)skip) != 0) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *s_vals = reinterpret_cast<double *>(smem_raw);
+  int *s_idx = reinterpret_cast<int *>(s_vals + SPMV3_STAGES * SPMV3_CAP);
+  int4 *s_desc = reinterpret_cast<int4 *>(s_idx + SPMV3_STAGES * SPMV3_CAP);
+  uint64_t *s_full = reinterpret_cast<uint64_t *>(s_desc + SPMV3_STAGES * SPMV3_NCW);
+  uint64_t *s_empty = s_full + SPMV3_STAGES;
+  double *s_red = reinterpret_cast<double *>(s_empty + SPMV3_STAGES);
+  double *s_out = s_red + 64;  // per consumer warp: the row sums of its warp-tile, by row number
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int g_begin = cta_begin[blockIdx.x];  // in groups of SPMV3_NCW warp-tiles
+  const int nt = cta_begin[blockIdx.x + 1] - g_begin;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < SPMV3_STAGES; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], SPMV3_NCW);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  double dot_acc = 0.0;
+  if (wid == 0) {
+    // ------------------------------------------------ producer (one elected lane)
+    if (lane == 0) {
+      const uint64_t pol = l2_policy_evict_first();
+      const int4 *g = wt + (size_t)g_begin * SPMV3_NCW;
+      int ka_n = 0, ke_n = 0;
+      if (nt > 0) {
+        ka_n = __ldg(&g[0].y) & ~3;
+        const int4 l = __ldg(&g[SPMV3_NCW - 1]);
+        ke_n = l.y + l.z;
+      }
+      for (int i = 0; i < nt; ++i) {
+        const int st = i % SPMV3_STAGES, use = i / SPMV3_STAGES;
+        const int ka = ka_n, cnt = (ke_n - ka_n + 3) & ~3;
+        if (i + 1 < nt) {  // next group's extent: issued before the wait below, so its latency hides
+          ka_n = __ldg(&g[(size_t)(i + 1) * SPMV3_NCW].y) & ~3;
+          const int4 l = __ldg(&g[(size_t)(i + 2) * SPMV3_NCW - 1]);
+          ke_n = l.y + l.z;
+        }
+        if (use > 0) mbar_wait(&s_empty[st], (unsigned)((use - 1) & 1));
+        mbar_expect_tx(&s_full[st], (unsigned)cnt * 12u + (unsigned)(SPMV3_NCW * 16));
+        tma_load_1d(s_desc + (size_t)st * SPMV3_NCW, g + (size_t)i * SPMV3_NCW, SPMV3_NCW * 16,
+                    &s_full[st], pol);
+        tma_load_1d(s_idx + (size_t)st * SPMV3_CAP, colidx + ka, (unsigned)cnt * 4u, &s_full[st], pol);
+        tma_load_1d(s_vals + (size_t)st * SPMV3_CAP, vals + ka, (unsigned)cnt * 8u, &s_full[st], pol);
+      }
+    }
+  } else {
+    // ------------------------------------------------ consumers: one warp-tile per warp per stage
+    const int cw = wid - 1;
+    double *ws = s_out + cw * SPMV3_WT;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned le = lt | (1u << lane);
+    const int sw = (lane >> 2) & 1;
+    for (int i = 0; i < nt; ++i) {
+      const int st = i % SPMV3_STAGES;
+      const unsigned par = (unsigned)((i / SPMV3_STAGES) & 1);
+      mbar_wait(&s_full[st], par);
+      const int4 dsc = s_desc[st * SPMV3_NCW + cw];
+      const int ka = s_desc[st * SPMV3_NCW].y & ~3;
+      const int row0 = dsc.x, k0 = dsc.y, cnt = dsc.z;
+      const int kend = k0 + cnt;
+      const int kb = (k0 & ~3) + 4 * lane;  // global index of this lane's first entry
+      int4 iv = make_int4(0, 0, 0, 0);
+      double2 t0 = make_double2(0.0, 0.0), t1 = make_double2(0.0, 0.0);
+      const bool any = (kb < kend) && (kb + 4 > k0);
+      if (any) {
+        const int e = kb - ka;
+        iv = *reinterpret_cast<const int4 *>(s_idx + (size_t)st * SPMV3_CAP + e);
+        t0 = *reinterpret_cast<const double2 *>(s_vals + (size_t)st * SPMV3_CAP + e + 2 * sw);
+        t1 = *reinterpret_cast<const double2 *>(s_vals + (size_t)st * SPMV3_CAP + e + 2 - 2 * sw);
+      }
+      const bool v0 = any && (kb >= k0), v1 = any && (kb + 1 >= k0) && (kb + 1 < kend),
+                 v2 = any && (kb + 2 >= k0) && (kb + 2 < kend), v3 = any && (kb + 3 < kend);
+      const bool g0 = v0 && !(iv.x & SPMV3_SKIP), g1 = v1 && !(iv.y & SPMV3_SKIP),
+                 g2 = v2 && !(iv.z & SPMV3_SKIP), g3 = v3 && !(iv.w & SPMV3_SKIP);
+      // 4 independent gathers in flight per lane
+      const double x0 = g0 ? gather_ld(&x[iv.x & 0x3fffffff]) : 0.0;
+      const double x1 = g1 ? gather_ld(&x[iv.y & 0x3fffffff]) : 0.0;
+      const double x2 = g2 ? gather_ld(&x[iv.z & 0x3fffffff]) : 0.0;
+      const double x3 = g3 ? gather_ld(&x[iv.w & 0x3fffffff]) : 0.0;
+      // the stage's bytes are in registers (the gather addresses depend on them): hand it back
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[st]);
+      if (cnt == 0) continue;  // padding descriptor (warp-uniform)
+      const int nrows_w = dsc.w;
+      // epilogue operands of the first two rounds (rows row0 + lane, row0 + lane + 32): in flight
+      // together with the gathers
+      double pd0 = 0.0, pd1 = 0.0, pv0 = 0.0, pv1 = 0.0, pi0 = 0.0, pi1 = 0.0;
+      {
+        const bool r0ok = lane < nrows_w, r1ok = lane + 32 < nrows_w;
+        if (POST != B200_POST_NONE) {
+          if (r0ok) pd0 = d[row0 + lane];
+          if (r1ok) pd1 = d[row0 + lane + 32];
+        }
+        if (POST == B200_POST_FMA_DOT || POST == B200_POST_FMA) {
+          if (r0ok) pv0 = v[row0 + lane];
+          if (r1ok) pv1 = v[row0 + lane + 32];
+        }
+        if (init != nullptr) {
+          if (r0ok) pi0 = init[row0 + lane];
+          if (r1ok) pi1 = init[row0 + lane + 32];
+        }
+      }
+
+      const double a0 = sw ? t1.x : t0.x, a1 = sw ? t1.y : t0.y;
+      const double a2 = sw ? t0.x : t1.x, a3 = sw ? t0.y : t1.y;
+      const bool e0 = v0 && (iv.x < 0), e1 = v1 && (iv.y < 0), e2 = v2 && (iv.z < 0), e3 = v3 && (iv.w < 0);
+      const unsigned b0 = __ballot_sync(FULL, e0), b1 = __ballot_sync(FULL, e1);
+      const unsigned b2 = __ballot_sync(FULL, e2), b3 = __ballot_sync(FULL, e3);
+      const unsigned ends = b0 | b1 | b2 | b3;  // lanes in which at least one row ends
+      // row number (within the warp-tile) of the first END of this lane = number of ENDs in the lanes before it
+      int r = __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
+      // open-row segments: the tail of lane h (the last lane <= me in which a row ends) starts the
+      // row that is open when my entries begin
+      const unsigned mle = ends & le;
+      const int h = mle ? 31 - __clz(mle) : 0;
+      const int maxdist = __reduce_max_sync(FULL, lane - h);
+
+      const double p0 = g0 ? __dmul_rn(a0, x0) : 0.0, p1 = g1 ? __dmul_rn(a1, x1) : 0.0;
+      const double p2 = g2 ? __dmul_rn(a2, x2) : 0.0, p3 = g3 ? __dmul_rn(a3, x3) : 0.0;
+      // in-lane sequential sums, restarted after every END (0 + p is exact)
+      double acc = p0;
+      double o0 = acc;
+      if (e0) acc = 0.0;
+      acc = __dadd_rn(acc, p1);
+      double o1 = acc;
+      if (e1) acc = 0.0;
+      acc = __dadd_rn(acc, p2);
+      double o2 = acc;
+      if (e2) acc = 0.0;
+      acc = __dadd_rn(acc, p3);
+      double o3 = acc;
+      if (e3) acc = 0.0;
+      // segmented inclusive scan of the tails (Hillis-Steele, fixed order)
+      double I = acc;
+      for (int dd = 1; dd <= maxdist; dd <<= 1) {
+        const double up = __shfl_up_sync(FULL, I, dd);
+        if (lane - dd >= h) I = __dadd_rn(up, I);
+      }
+      double carry = __shfl_up_sync(FULL, I, 1);
+      if (lane == 0) carry = 0.0;  // warp-tiles hold whole rows: nothing is open at entry 0
+      // the first END of the lane closes the row that was open on entry
+      if (e0) o0 = __dadd_rn(carry, o0);
+      else if (e1) o1 = __dadd_rn(carry, o1);
+      else if (e2) o2 = __dadd_rn(carry, o2);
+      else if (e3) o3 = __dadd_rn(carry, o3);
+      // transpose through the warp's scratch: row sums by row number, then a COALESCED epilogue
+      // (one row per lane and round: full-sector stores of y, one division per row, operands of the
+      // first two rounds were fetched before the gathers were consumed)
+      if (e0) { ws[r] = o0; ++r; }
+      if (e1) { ws[r] = o1; ++r; }
+      if (e2) { ws[r] = o2; ++r; }
+      if (e3) { ws[r] = o3; }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < SPMV3_WT / 32; ++j) {
+        const int rr = lane + 32 * j;
+        if (j * 32 >= nrows_w) break;  // warp-uniform
+        if (rr < nrows_w) {
+          const int row = row0 + rr;
+          double sres = ws[rr];
+          double dv, vv, iv0;
+          if (j == 0) { dv = pd0; vv = pv0; iv0 = pi0; }
+          else if (j == 1) { dv = pd1; vv = pv1; iv0 = pi1; }
+          else {
+            dv = (POST != B200_POST_NONE) ? d[row] : 0.0;
+            vv = (POST == B200_POST_FMA_DOT || POST == B200_POST_FMA) ? v[row] : 0.0;
+            iv0 = (init != nullptr) ? init[row] : 0.0;
+          }
+          if (init != nullptr) sres = __dadd_rn(sres, init_sign * iv0);
+          spmv_epilogue_pre<POST>(sres, row, y, dv, vv, dot_acc);
+        }
+      }
+      __syncwarp();  // the scratch is rewritten by the next warp-tile
+    }
+  }
+
+  if (hook == B200_HOOK_P2P_SIGNAL) {
+    // multi-GPU: tell every peer that this rank's partial product is complete (last block only)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned tk = atomicAdd(counter, 1u);
+      if (tk == gridDim.x - 1) {
+        *counter = 0u;
+        __threadfence_system();
+        const B200P2pSignal *ps = reinterpret_cast<const B200P2pSignal *>(hook_arg);
+        for (int r = 0; r < ps->nranks; ++r)
+          if (r != ps->rank) *((volatile unsigned long long *)(ps->flags[r] + ps->rank)) = hook_val;
+      }
+    }
+  }
+
+  if (POST == B200_POST_FMA_DOT) {
+    double accd[1] = {dot_acc};
+    block_sum<1>(accd, s_red);
+    if (grid_finish<1>(accd, partials, counter, 0u, s_red)) {
+      if (tid == 0) {
+        *dot_out = accd[0];
+        if (hook == B200_HOOK_CG_ALPHA) {
+          B200CgCtl *c = reinterpret_cast<B200CgCtl *>(hook_arg);
+          c->pGp = accd[0];
+          c->alpha = c->ztr / accd[0];
+        }
+      }
+    }
+  }
+}
+
+// ---- host side of v3: the flagged stream, its warp-tiles and the static CTA partition.
+// Pure host code (no CUDA calls): also exported for the CPU tests (tests/test_spmv_plan_cpu.py
+// re-executes the kernel's lane algorithm on this plan in numpy).
+struct Spmv3Plan {
+  std::vector<int> rowptr;   // stored row pointers (every row has >= 1 stored entry)
+  std::vector<int> idx;      // column | END | SKIP
+  std::vector<double> vals;
+  std::vector<int4> wt;      // padded per CTA to a multiple of SPMV3_NCW: {row0, k0, cnt, nrows}
+  std::vector<int> cta_begin;  // grid+1, in groups of SPMV3_NCW descriptors
+  int grid = 0;
+  int nwt = 0;               // real warp-tiles
+};
+
+static bool spmv3_build_plan(int nrows, int ncols, const int *rp, const int *ci, const double *va,
+                             int grid_cap, Spmv3Plan &P) {
+  if (nrows <= 0 || ncols >= (1 << 30)) return false;
+  const long long nnz = rp[nrows];
+  long long empties = 0;
+  for (int r = 0; r < nrows; ++r) {
+    const int len = rp[r + 1] - rp[r];
+    if (len > SPMV3_MAXROW) return false;
+    if (len == 0) ++empties;
+  }
+  const long long stored = nnz + empties;
+  if (stored > 2000000000LL) return false;
+  P.rowptr.resize((size_t)nrows + 1);
+  P.idx.resize((size_t)stored);
+  P.vals.resize((size_t)stored);
+  int pos = 0;
+  for (int r = 0; r < nrows; ++r) {
+    P.rowptr[r] = pos;
+    const int a = rp[r], b = rp[r + 1];
+    if (a == b) {
+      P.idx[pos] = (int)(SPMV3_END | SPMV3_SKIP);
+      P.vals[pos] = 0.0;
+      ++pos;
+    } else {
+      for (int k = a; k < b; ++k) {
+        P.idx[pos] = ci[k];
+        P.vals[pos] = va[k];
+        ++pos;
+      }
+      P.idx[pos - 1] = (int)((unsigned)P.idx[pos - 1] | SPMV3_END);
+    }
+  }
+  P.rowptr[nrows] = pos;
+  // warp-tiles: whole rows, aligned span (k0 & ~3 .. end) <= 128 entries
+  std::vector<int4> real;
+  real.reserve((size_t)(stored / 100 + 16));
+  for (int r = 0; r < nrows;) {
+    const int k0 = P.rowptr[r], base = k0 & ~3;
+    int r1 = r;
+    while (r1 < nrows && P.rowptr[r1 + 1] - base <= SPMV3_WT) ++r1;
+    int4 t;
+    t.x = r;
+    t.y = k0;
+    t.z = P.rowptr[r1] - k0;
+    t.w = r1 - r;
+    real.push_back(t);
+    r = r1;
+  }
+  P.nwt = (int)real.size();
+  int grid = grid_cap < P.nwt ? grid_cap : P.nwt;
+  if (grid < 1) grid = 1;
+  P.grid = grid;
+  P.cta_begin.assign((size_t)grid + 1, 0);
+  P.wt.clear();
+  P.wt.reserve(real.size() + (size_t)grid * SPMV3_NCW);
+  for (int c = 0; c < grid; ++c) {
+    const long long a = (long long)P.nwt * c / grid, b = (long long)P.nwt * (c + 1) / grid;
+    for (long long w = a; w < b; ++w) P.wt.push_back(real[(size_t)w]);
+    // pad the CTA's list to whole groups with empty descriptors that continue the entry range
+    const int4 last = real[(size_t)(b - 1)];
+    while (P.wt.size() % SPMV3_NCW != 0) {
+      int4 t;
+      t.x = last.x + last.w;
+      t.y = last.y + last.z;
+      t.z = 0;
+      t.w = 0;
+      P.wt.push_back(t);
+    }
+    P.cta_begin[(size_t)c + 1] = (int)(P.wt.size() / SPMV3_NCW);
+  }
+  return true;
+}
+
+// C view of a plan for the tests (host memory, owned by the handle)
+struct B200Spmv3PlanHost {
+  Spmv3Plan plan;
+};
+extern "C" B200Spmv3PlanHost *b200_spmv3_plan_build(int nrows, int ncols, const int *rp, const int *ci,
+                                                    const double *va, int grid_cap) {
+  B200Spmv3PlanHost *h = new B200Spmv3PlanHost();
+  if (!spmv3_build_plan(nrows, ncols, rp, ci, va, grid_cap, h->plan)) {
+    delete h;
+    return nullptr;
+  }
+  return h;
+}
+extern "C" void b200_spmv3_plan_free(B200Spmv3PlanHost *h) { delete h; }
+extern "C" int b200_spmv3_plan_info(const B200Spmv3PlanHost *h, int *stored, int *nwt, int *ndesc, int *grid,
+                                    int *ncw) {
+  *stored = (int)h->plan.idx.size();
+  *nwt = h->plan.nwt;
+  *ndesc = (int)h->plan.wt.size();
+  *grid = h->plan.grid;
+  *ncw = SPMV3_NCW;
+  return 0;
+}
+extern "C" const int *b200_spmv3_plan_rowptr(const B200Spmv3PlanHost *h) { return h->plan.rowptr.data(); }
+extern "C" const int *b200_spmv3_plan_idx(const B200Spmv3PlanHost *h) { return h->plan.idx.data(); }
+extern "C" const double *b200_spmv3_plan_vals(const B200Spmv3PlanHost *h) { return h->plan.vals.data(); }
+extern "C" const int *b200_spmv3_plan_desc(const B200Spmv3PlanHost *h) {
+  return reinterpret_cast<const int *>(h->plan.wt.data());
+}
+extern "C" const int *b200_spmv3_plan_cta_begin(const B200Spmv3PlanHost *h) { return h->plan.cta_begin.data(); }
+
 // ------------------------------------------------------------------ host side
 static int lanes_log2_for(int max_row_nnz) {
   if (max_row_nnz <= 16) return 0;
@@ -551,24 +950,102 @@ static int lanes_log2_for(int max_row_nnz) {
   return 5;
 }
 
+static void spmv_set_attrs() {
+  static bool attr_done = false;
+  if (attr_done) return;
+#define SET_ATTR(K, BYTES)                                                                       \
+  do {                                                                                           \
+    cudaFuncSetAttribute(K<B200_POST_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES));    \
+    cudaFuncSetAttribute(K<B200_POST_DIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES));     \
+    cudaFuncSetAttribute(K<B200_POST_FMA_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES)); \
+    cudaFuncSetAttribute(K<B200_POST_FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES));     \
+  } while (0)
+  SET_ATTR(spmv_csr_stream_kernel, spmv_smem_bytes());
+  SET_ATTR(spmv_ws_kernel, spmv2_smem_bytes());
+  SET_ATTR(spmv_flag_kernel, spmv3_smem_bytes());
+#undef SET_ATTR
+  attr_done = true;
+}
+
+// v3: upload the flagged stream (it IS the operator's CSR: rowptr / colidx / vals stay a valid CSR with
+// explicit zeros, flags in the two top bits of colidx) plus the warp-tile descriptors
+static int spmv_upload_v3(B200Spmv *M, const Spmv3Plan &P) {
+  const size_t stored = P.idx.size();
+  const size_t pad = ((stored + 3) & ~(size_t)3) + 8;
+  M->stored = (long long)stored;
+  M->grid = P.grid;
+  M->ntiles = P.nwt;
+  M->tile_nnz = SPMV3_WT;
+  M->d_rowptr = (int *)b200_malloc((size_t)(M->nrows + 1 + 8) * 4);
+  M->d_colidx = (int *)b200_malloc(pad * 4);
+  M->d_vals = (double *)b200_malloc(pad * 8);
+  M->d_wt3 = (int4 *)b200_malloc(P.wt.size() * sizeof(int4));
+  M->d_cta_begin3 = (int *)b200_malloc(P.cta_begin.size() * 4);
+  M->d_partials = (double *)b200_malloc((size_t)B200_MAX_PARTIALS * 8);
+  M->d_counter = (unsigned int *)b200_malloc(64);
+  if (!M->d_rowptr || !M->d_colidx || !M->d_vals || !M->d_wt3 || !M->d_cta_begin3 || !M->d_partials ||
+      !M->d_counter)
+    return -1;
+  int rc = 0;
+  rc |= b200_memset0(M->d_rowptr, (size_t)(M->nrows + 1 + 8) * 4);
+  rc |= b200_memset0(M->d_colidx, pad * 4);
+  rc |= b200_memset0(M->d_vals, pad * 8);
+  rc |= b200_memset0(M->d_counter, 64);
+  rc |= b200_h2d(M->d_rowptr, P.rowptr.data(), (size_t)(M->nrows + 1) * 4);
+  rc |= b200_h2d(M->d_colidx, P.idx.data(), stored * 4);
+  rc |= b200_h2d(M->d_vals, P.vals.data(), stored * 8);
+  rc |= b200_h2d(M->d_wt3, P.wt.data(), P.wt.size() * sizeof(int4));
+  rc |= b200_h2d(M->d_cta_begin3, P.cta_begin.data(), P.cta_begin.size() * 4);
+  rc |= b200_sync();  // the plan's host vectors go out of scope
+  if (rc != 0) return -1;
+  spmv_set_attrs();
+  return 0;
+}
+
 extern "C" B200Spmv *b200_spmv_create(int nrows, int ncols, const int *h_rowptr,
                                       const int *h_colidx, const double *h_vals) {
   if (b200_runtime_init() != 0) return nullptr;
+  if (ncols >= (1 << 30) || nrows >= (1 << 30)) {
+    // bits 30/31 of the stored column indices are flags (v3); every reader masks them
+    b200_set_error("b200_spmv_create: dimensions >= 2^30 are not supported", cudaErrorInvalidValue, __FILE__,
+                   __LINE__);
+    return nullptr;
+  }
   B200Spmv *M = (B200Spmv *)calloc(1, sizeof(B200Spmv));
   if (!M) return nullptr;
   M->nrows = nrows;
   M->ncols = ncols;
   M->nnz = h_rowptr[nrows];
+  M->stored = M->nnz;
   const long long nnz = M->nnz;
   const int nsm = b200_num_sms();
 
-  // tile size: full tiles for big matrices, smaller ones so that small matrices
-  // still spread over all SMs
   {
     const char *e = getenv("SCS_B200_SPMV");
     M->version = e ? atoi(e) : SPMV_DEFAULT_VERSION;
-    if (M->version != 1 && M->version != 2) M->version = SPMV_DEFAULT_VERSION;
+    if (M->version < 1 || M->version > 3) M->version = SPMV_DEFAULT_VERSION;
   }
+  if (M->version == 3) {
+    // flagged stream; operators with a row longer than SPMV3_MAXROW keep the plain CSR + v2 kernel
+    int cap = SPMV3_CTAS_PER_SM * nsm;
+    const char *g = getenv("SCS_B200_SPMV_GRID");  // tests: force many groups per CTA on small matrices
+    if (g && atoi(g) > 0 && atoi(g) < cap) cap = atoi(g);
+    // operators with very short rows (avg below SCS_B200_SPMV_MINAVG, default 0 = never) can be sent to
+    // the row-per-lane kernel instead (tuning knob, see profiles/README.md)
+    const char *ma = getenv("SCS_B200_SPMV_MINAVG");
+    const bool too_short = ma && nrows > 0 && (double)nnz / nrows < atof(ma);
+    Spmv3Plan P;
+    if (nrows > 0 && !too_short && spmv3_build_plan(nrows, ncols, h_rowptr, h_colidx, h_vals, cap, P)) {
+      if (spmv_upload_v3(M, P) != 0) {
+        b200_spmv_destroy(M);
+        return nullptr;
+      }
+      return M;
+    }
+    M->version = 2;
+  }
+  // tile size: full tiles for big matrices, smaller ones so that small matrices
+  // still spread over all SMs
   const int max_tile = M->version == 2 ? SPMV2_TILE_NNZ : SPMV_TILE_NNZ;
   const int ctas_per_sm = M->version == 2 ? SPMV2_CTAS_PER_SM : SPMV_CTAS_PER_SM;
   long long want = nnz / (2LL * ctas_per_sm * nsm);
@@ -694,26 +1171,7 @@ extern "C" B200Spmv *b200_spmv_create(int nrows, int ncols, const int *h_rowptr,
     b200_spmv_destroy(M);
     return nullptr;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(spmv_csr_stream_kernel<B200_POST_NONE>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spmv_smem_bytes());
-    cudaFuncSetAttribute(spmv_csr_stream_kernel<B200_POST_DIV>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spmv_smem_bytes());
-    cudaFuncSetAttribute(spmv_csr_stream_kernel<B200_POST_FMA_DOT>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spmv_smem_bytes());
-    cudaFuncSetAttribute(spmv_csr_stream_kernel<B200_POST_FMA>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spmv_smem_bytes());
-    cudaFuncSetAttribute(spmv_ws_kernel<B200_POST_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)spmv2_smem_bytes());
-    cudaFuncSetAttribute(spmv_ws_kernel<B200_POST_DIV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)spmv2_smem_bytes());
-    cudaFuncSetAttribute(spmv_ws_kernel<B200_POST_FMA_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)spmv2_smem_bytes());
-    cudaFuncSetAttribute(spmv_ws_kernel<B200_POST_FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)spmv2_smem_bytes());
-    attr_done = true;
-  }
+  spmv_set_attrs();
   return M;
 }
 
@@ -726,6 +1184,8 @@ extern "C" void b200_spmv_destroy(B200Spmv *M) {
   b200_free(M->d_cta_tile_begin);
   b200_free(M->d_partials);
   b200_free(M->d_counter);
+  b200_free(M->d_wt3);
+  b200_free(M->d_cta_begin3);
   free(M);
 }
 
@@ -743,15 +1203,19 @@ extern "C" double b200_spmv_alg_bytes(const B200Spmv *M, int extra_row_vectors) 
 extern "C" int b200_spmv(const B200Spmv *M, const B200SpmvArgs *a) {
   if (M->nrows == 0) return 0;
   cudaStream_t st = (cudaStream_t)b200_stream();
-  const size_t smem = M->version == 2 ? spmv2_smem_bytes() : spmv_smem_bytes();
-  dim3 grid(M->grid), block(M->version == 2 ? SPMV2_THREADS : SPMV_THREADS);
-#define ARGS                                                                                   \
-  M->d_rowptr, M->d_colidx, M->d_vals, M->d_tiles, M->d_cta_tile_begin, a->d_x, a->d_y,        \
-      a->d_init, a->init_sign, a->d_d, a->d_v, a->d_dot, a->hook, a->d_hook_arg, a->d_skip,    \
-      M->d_partials, M->d_counter, a->hook_val
+  const size_t smem = M->version == 3 ? spmv3_smem_bytes()
+                                      : (M->version == 2 ? spmv2_smem_bytes() : spmv_smem_bytes());
+  dim3 grid(M->grid), block(M->version == 3 ? SPMV3_THREADS : (M->version == 2 ? SPMV2_THREADS : SPMV_THREADS));
+#define TAIL                                                                                   \
+  a->d_x, a->d_y, a->d_init, a->init_sign, a->d_d, a->d_v, a->d_dot, a->hook, a->d_hook_arg,   \
+      a->d_skip, M->d_partials, M->d_counter, a->hook_val
+#define ARGS M->d_rowptr, M->d_colidx, M->d_vals, M->d_tiles, M->d_cta_tile_begin, TAIL
 #define LAUNCH(POSTV)                                                                          \
   do {                                                                                         \
-    if (M->version == 2) spmv_ws_kernel<POSTV><<<grid, block, smem, st>>>(ARGS);               \
+    if (M->version == 3)                                                                       \
+      spmv_flag_kernel<POSTV><<<grid, block, smem, st>>>(M->d_colidx, M->d_vals, M->d_wt3,     \
+                                                         M->d_cta_begin3, TAIL);               \
+    else if (M->version == 2) spmv_ws_kernel<POSTV><<<grid, block, smem, st>>>(ARGS);          \
     else spmv_csr_stream_kernel<POSTV><<<grid, block, smem, st>>>(ARGS);                       \
   } while (0)
   switch (a->post) {
@@ -763,10 +1227,13 @@ extern "C" int b200_spmv(const B200Spmv *M, const B200SpmvArgs *a) {
   }
 #undef LAUNCH
 #undef ARGS
+#undef TAIL
   b200_count_launch(1);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
+extern "C" int b200_spmv_version(const B200Spmv *M) { return M->version; }
+extern "C" long long b200_spmv_stored(const B200Spmv *M) { return M->stored; }
 
 // Alternating launches of two operators (A then A'), every launch bracketed by its own CUDA
 // events on the library stream: the other operator's matrix stream evicts this one's from L2,

@@ -2,6 +2,7 @@
 UNMODIFIED reference CPU-indirect backend (oracle/_ref/libscsindir_ref.so),
 called through the same five-symbol C ABI (reference include/linsys.h:25-71)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -70,9 +71,63 @@ def test_spmv_matches_reference(lib, reflib, m, n, col_nnz, z, seed):
             reflib._scs_accum_by_atrans(C.byref(hp.A), capi.dptr(yv), capi.dptr(ref))
             scale = np.abs(ref).max() + 1e-300
             assert np.abs(mine - ref).max() / scale <= 1e-13
-            if col_nnz <= 16:
-                # short rows run the same sequential fma chain as the CPU loop
+            if col_nnz <= 16 and os.environ.get("SCS_B200_SPMV") == "2":
+                # row-per-lane kernel (v2): short rows run the same sequential chain as the CPU loop
                 assert np.array_equal(mine, ref), "A'x not bit-identical for short rows"
+    finally:
+        lib.scs_free_lin_sys_work(w)
+
+
+def ragged_csc(m, n, rng, mean_nnz, p_empty_col=0.1, max_col=120):
+    """CSC with ragged columns (some empty, some long) and, for small mean_nnz, many empty rows."""
+    lens = np.minimum(rng.poisson(mean_nnz, n), min(m, max_col))
+    lens[rng.random(n) < p_empty_col] = 0
+    lens[rng.random(n) < 0.02] = min(m, max_col)
+    cols = np.repeat(np.arange(n, dtype=np.int64), lens)
+    keys = np.unique(cols * m + rng.integers(0, m, size=cols.size))  # sorted (col, row), duplicates dropped
+    cols, rows = keys // m, keys % m
+    indptr = np.zeros(n + 1, dtype=np.int32)
+    indptr[1:] = np.cumsum(np.bincount(cols, minlength=n))
+    data = rng.uniform(-1.0, 1.0, size=rows.size)
+    return data, rows.astype(np.int32), indptr, (m, n)
+
+
+@pytest.mark.parametrize("grid_cap", [None, 1, 3])
+@pytest.mark.parametrize("m,n,mean_nnz,seed", [(5000, 3000, 2.0, 11), (200000, 30000, 12.0, 12), (300, 4000, 1.0, 13)])
+def test_spmv_flagged_stream_ragged(lib, reflib, m, n, mean_nnz, seed, grid_cap, monkeypatch):
+    """v3 kernel on ragged operators (empty rows -> explicit zeros, rows ending inside / across lanes),
+    also with the grid forced to 1 / 3 CTAs so that every CTA walks many groups (ring wrap-around)."""
+    if grid_cap is not None:
+        monkeypatch.setenv("SCS_B200_SPMV_GRID", str(grid_cap))
+    rng = np.random.default_rng(seed)
+    A = ragged_csc(m, n, rng, mean_nnz)
+    hp = capi.HostProblem(A, np.zeros(m), np.zeros(n), {"l": m})
+    dr = diag_r_for(n, m, 0)
+    w = lib.scs_init_lin_sys_work(C.byref(hp.A), None, capi.dptr(dr))
+    assert w
+    try:
+        for rep in range(3):
+            x = rng.standard_normal(n)
+            yv = rng.standard_normal(m)
+            for acc in (0, 1):
+                y0 = rng.standard_normal(m) if acc else np.zeros(m)
+                mine, ref = y0.copy(), y0.copy()
+                assert lib.scs_b200_accum_by_a(w, capi.dptr(x), capi.dptr(mine), acc) == 0
+                reflib._scs_accum_by_a(C.byref(hp.A), capi.dptr(x), capi.dptr(ref))
+                assert np.abs(mine - ref).max() / (np.abs(ref).max() + 1e-300) <= 1e-13
+                x0 = rng.standard_normal(n) if acc else np.zeros(n)
+                mine, ref = x0.copy(), x0.copy()
+                assert lib.scs_b200_accum_by_atrans(w, capi.dptr(yv), capi.dptr(mine), acc) == 0
+                reflib._scs_accum_by_atrans(C.byref(hp.A), capi.dptr(yv), capi.dptr(ref))
+                assert np.abs(mine - ref).max() / (np.abs(ref).max() + 1e-300) <= 1e-13
+        # and a full KKT solve through the same operators (POST_DIV / POST_FMA_DOT epilogues, init chains)
+        rhs = rng.standard_normal(n + m)
+        wr = reflib.scs_init_lin_sys_work(C.byref(hp.A), None, capi.dptr(dr))
+        mine, ref = rhs.copy(), rhs.copy()
+        assert lib.scs_solve_lin_sys(w, capi.dptr(mine), None, 1e-12) == 0
+        assert reflib.scs_solve_lin_sys(wr, capi.dptr(ref), None, 1e-12) == 0
+        reflib.scs_free_lin_sys_work(wr)
+        assert np.abs(mine - ref).max() / np.abs(ref).max() <= 1e-10
     finally:
         lib.scs_free_lin_sys_work(w)
 

@@ -175,13 +175,22 @@ def run_reference(args, iters, lib, omp_threads, blas_threads=1):
 
 
 def best_reference(args, iters, probe_iters=2):
-    """The reference with 'all the host threads it can use': probe a few thread configurations of
-    its single-threaded and OpenMP builds on a short run and keep the fastest for the real sample."""
+    """The reference with 'all the host threads it can use'. Only accum_by_atrans is parallel in the
+    reference (OpenMP, linsys/scs_matrix.c:174-176); probing on this pool's hosts (profiles/README.md: 1, 8,
+    32, 128 threads) showed 32 threads fastest and all 128 hardware threads 6x SLOWER, so the default is
+    min(32, cores) without probing -- a probe costs minutes at C2 (one reference iteration takes ~10 s).
+    SCS_BENCH_PROBE=1 repeats the probe."""
     d = os.path.join(ROOT, "oracle", "_ref")
     plain, omp = os.path.join(d, "libscsindir_ref.so"), os.path.join(d, "libscsindir_ref_omp.so")
     if not os.path.exists(plain):
         return None
     ncores = os.cpu_count() or 1
+    if not os.environ.get("SCS_BENCH_PROBE"):
+        lib, t = (omp, min(32, ncores)) if os.path.exists(omp) else (plain, 1)
+        r = run_reference(args, iters, lib, t, 1)
+        r["cores"] = t
+        r["probes"] = "not probed (SCS_BENCH_PROBE=1 to probe; earlier probes: profiles/README.md)"
+        return r
     cands = [(plain, 1, 1)]
     if os.path.exists(omp):
         for t in sorted({min(8, ncores), min(32, ncores), ncores}):
@@ -200,6 +209,16 @@ def best_reference(args, iters, probe_iters=2):
     r["cores"] = best["omp_threads"]
     r["probes"] = [{"lib": q["lib"], "threads": q["omp_threads"], "its_per_s": q["its_per_s"]} for q in probes]
     return r
+
+
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/spmv_ncu_traffic.json, written from gpurun_out by scripts/ncu_summary.py), or None."""
+    p = os.path.join(ROOT, "profiles", "spmv_ncu_traffic.json")
+    try:
+        return float(json.load(open(p))[kernel_key]["dram_bytes_per_launch"])
+    except Exception:
+        return None
 
 
 def main():
@@ -228,15 +247,16 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        probe = best_reference(args, 2)
-        if probe is None:
+        # bounded sample: a reference iteration of C2 takes ~10 s on this pool's hosts, so K is capped
+        # (SCS_BENCH_REF_ITERS) to keep the arm within a few minutes; small configs run all K steps
+        big = args.scale >= 0.5 and args.config != "C1"
+        k = int(min(args.steps, int(os.environ.get("SCS_BENCH_REF_ITERS", "6")))) if big else int(args.steps)
+        k = max(k, 2)
+        r = best_reference(args, k)
+        if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}))
             return 0
-        budget_s = float(os.environ.get("SCS_BENCH_REF_BUDGET_S", "120"))
-        k = int(max(3, min(args.steps, budget_s * probe["its_per_s"])))
-        lib_path = os.path.join(ROOT, "oracle", "_ref", probe["lib"])
-        r = run_reference(args, k, lib_path, probe["omp_threads"], probe["blas_threads"])
-        r["cores"] = probe["omp_threads"]
+        probe = {"probes": r["probes"]}
         prob = {"n": r["n"], "m": r["m"], "nnz": r["nnz"]}
         out = dict(base)
         out.update({
@@ -246,7 +266,7 @@ def main():
                        "n": prob["n"], "m": prob["m"], "nnz": prob["nnz"], "settings": "SCS defaults, eps=0"},
             "cpu_baseline": {"value": r["its_per_s"], "unit": "iters/s", "cores": r["cores"], "kind": "reference",
                              "sample": f"{r['iters']} ADMM iterations of the unmodified reference CPU-indirect "
-                                       f"solver ({r['lib']}, OMP_NUM_THREADS={r['cores']}, fastest of "
+                                       f"solver ({r['lib']}, OMP_NUM_THREADS={r['cores']}; thread choice: "
                                        f"{probe['probes']}) on the full workload"},
             "e2e": {"value": r["e2e_its_per_s"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -348,8 +368,8 @@ def main():
         lw = lib.scs_init_lin_sys_work(C.byref(hp.A), None, capi.dptr(dr))
         ab = C.c_double(0.0)
         rows = []
-        for op, name in ((0, "spmv_csr_stream<POST_NONE> y=A x (rows of A, 3.3 nnz/row)"),
-                         (1, "spmv_csr_stream<POST_NONE> y=A'x (cols of A, 10 nnz/row)")):
+        for op, name in ((0, "spmv_flag_kernel<POST_NONE> y=A x (rows of A)"),
+                         (1, "spmv_flag_kernel<POST_NONE> y=A'x (columns of A)")):
             ms = lib.scs_b200_time_spmv(lw, op, 20, C.byref(ab))
             rows.append({"kernel": name, "ms": ms, "alg_bytes": ab.value, "achieved": ab.value / ms / 1e6,
                          "frac": ab.value / ms / 1e6 / peak})
@@ -359,18 +379,19 @@ def main():
         lib.scs_free_lin_sys_work(lw)
         dom = max(rows, key=lambda r: r["ms"])
         roof = {"bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
-                "traffic": None, "kernel": dom["kernel"], "ms_per_launch": dom["ms"],
+                "traffic": ncu_traffic("A x" if dom is rows[0] else "A'x") if (args.config == "C2" and args.scale == 1.0 and world == 1) else None,
+                "kernel": dom["kernel"], "ms_per_launch": dom["ms"],
                 "alg_bytes_per_launch": dom["alg_bytes"], "peak_source": peak_src,
                 "l2_flush": "alternating A / A' launches: 2 x matrix bytes > L2"}
         extra["roofline_all"] = rows + [cg_row]
         if not args.no_cpu_baseline and world == 1:
             try:
-                k = 6 if args.scale >= 0.5 else 40
+                k = (3 if args.config != "C1" else 40) if args.scale >= 0.5 else 40
                 r = best_reference(args, k)
                 if r:
                     cpu_base = {"value": r["its_per_s"], "unit": "iters/s", "cores": r["cores"], "kind": "reference",
                                 "sample": f"{r['iters']} ADMM iterations of the unmodified reference CPU-indirect "
-                                          f"solver ({r['lib']}, {r['cores']} threads, fastest of {r['probes']}) on the same "
+                                          f"solver ({r['lib']}, {r['cores']} threads; thread choice: {r['probes']}) on the same "
                                           f"workload (setup {r['init_s']:.1f}s excluded)"}
             except Exception as e:  # the checker must never break the measurement
                 cpu_base = {"value": None, "unit": "iters/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}

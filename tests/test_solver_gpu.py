@@ -90,6 +90,45 @@ def test_one_iteration_matches_reference(lib, reflib, kind):
         assert abs(a - b) <= 1e-9 * max(1.0, abs(b)), (kind, fld, a, b)
 
 
+def qp_problem(seed):
+    """min 1/2 x'Px + c'x s.t. Ax + s = b, s in K: P = B'B + 0.1 I, upper triangle in CSC as
+    include/scs.h:60-77 requires (reference QP path: accum_by_p, linsys/scs_matrix.c:206-225)."""
+    import scipy.sparse as sp
+    prob = problems.make_problem(400, 100, 8, {"z": 40, "l": 120, "q": [3, 7, 30, 200]}, seed)
+    rng = np.random.default_rng(seed + 1000)
+    n = prob["n"]
+    B = sp.random(30, n, density=0.08, random_state=np.random.RandomState(seed), format="csr")
+    P = sp.triu(B.T @ B + 0.1 * sp.identity(n), format="csc")
+    P.sort_indices()
+    prob = dict(prob)
+    prob["P"] = (P.data.copy(), P.indices.astype(np.int32), P.indptr.astype(np.int32), (n, n))
+    prob["opt"] = None
+    del rng
+    return prob
+
+
+def test_qp_matches_reference(lib, reflib):
+    """Quadratic objective through the device-resident driver: P in the CG operator and the
+    preconditioner, P x in the residuals, x'Px in the objective; one iteration sharp, converged loose."""
+    prob = qp_problem(21)
+    st_m, info_m, x, y, s = solve_with(lib, prob, max_iters=1)
+    st_r, info_r, xr, yr, sr = solve_with(reflib, prob, max_iters=1)
+    assert st_m == st_r and info_m.iter == info_r.iter == 1
+    for a, b, nm in ((x, xr, "x"), (y, yr, "y"), (s, sr, "s")):
+        err = np.abs(a - b).max() / max(1.0, np.abs(b).max())
+        assert err <= 1e-9, (nm, err)
+    for fld in ("pobj", "dobj", "res_pri", "res_dual", "gap"):
+        a, b = getattr(info_m, fld), getattr(info_r, fld)
+        assert abs(a - b) <= 1e-9 * max(1.0, abs(b)), (fld, a, b)
+    eps = 1e-7
+    st_m, info_m, x, y, s = solve_with(lib, prob, eps_abs=eps, eps_rel=eps, max_iters=30000)
+    st_r, info_r, xr, yr, sr = solve_with(reflib, prob, eps_abs=eps, eps_rel=eps, max_iters=30000)
+    print(f"\n[qp] mine it={info_m.iter} pobj={info_m.pobj:.10e} | ref it={info_r.iter} pobj={info_r.pobj:.10e}")
+    assert st_m == st_r == 1
+    assert abs(info_m.pobj - info_r.pobj) <= 100 * eps * max(1.0, abs(info_r.pobj))
+    assert np.abs(x - xr).max() <= 1e-4 * max(1.0, np.abs(xr).max())   # strictly convex in x: unique minimiser
+
+
 def test_c1_shape_default_settings(lib, reflib):
     """BASELINE configs[0]: n=1000, m=4000, 32 nnz/col SOCP at default eps=1e-4."""
     prob = problems.config("C1")

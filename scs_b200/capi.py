@@ -144,6 +144,10 @@ def make_cone(cone):
     if s is not None and len(s) > 0:
         keep["s"] = np.ascontiguousarray(s, dtype=np.int32)
         k.s, k.ssize = iptr(keep["s"]), len(keep["s"])
+    cs = cone.get("cs")
+    if cs is not None and len(cs) > 0:
+        keep["cs"] = np.ascontiguousarray(cs, dtype=np.int32)
+        k.cs, k.cssize = iptr(keep["cs"]), len(keep["cs"])
     k.ep = int(cone.get("ep", 0))
     k.ed = int(cone.get("ed", 0))
     p = cone.get("p")
@@ -158,7 +162,8 @@ def cone_rows(cone):
     s = cone.get("s", []) or []
     bs = (len(cone["bu"]) + 1) if cone.get("bu") is not None and len(cone["bu"]) else int(cone.get("bsize", 0))
     return (int(cone.get("z", 0)) + int(cone.get("l", 0)) + bs + int(sum(q)) +
-            int(sum(int(k) * (int(k) + 1) // 2 for k in s)) + 3 * (int(cone.get("ep", 0)) + int(cone.get("ed", 0))))
+            int(sum(int(k) * (int(k) + 1) // 2 for k in s)) +
+            3 * (int(cone.get("ep", 0)) + int(cone.get("ed", 0)) + len(cone.get("p", []) or [])))
 
 
 class _Decl:

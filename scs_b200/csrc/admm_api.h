@@ -83,6 +83,11 @@ typedef struct B200Cones B200Cones;
 B200Cones *b200_cones_create(int m, int nz, int nl, int bsize, const double *h_bl,
                              const double *h_bu, int qsize, const int *h_q, int ssize,
                              const int *h_s);
+/* exponential (ep primal, ed dual) and power (psize, parameters h_p, sign = primal/dual) triples: the
+ * last 3 (ep + ed + psize) rows of the cone product (kernels/cone_triples.cu) */
+int b200_cones_set_triples(B200Cones *c, int ep, int ed, int psize, const double *h_p);
+int b200_cone_triples_project(int n_exp_primal, int n_exp_dual, int n_pow, long long exp_off,
+                              const double *d_pow, double *d_x, const double *d_s, const double *d_ry);
 void b200_cones_destroy(B200Cones *c);
 /* Projects the box/SOC/PSD rows. On entry d_x (length m, the y block of u) holds
  * x = -r .* u on those rows and d_s holds the saved u (k_cone_pre); on exit

@@ -21,13 +21,15 @@ ScsB200ConeWork *scs_b200_init_cone(const ScsCone *k, scs_int m, const scs_float
   int j;
   long long dims;
   if (!k || m <= 0) return SCS_NULL;
-  if (k->cssize > 0 || k->ep > 0 || k->ed > 0 || k->psize > 0) {
-    fprintf(stderr, "scs_b200: complex-PSD / exponential / power cones are not supported\n");
+  if (k->cssize > 0) {
+    fprintf(stderr, "scs_b200: the complex-PSD cone is not supported\n");
     return SCS_NULL;
   }
+  if (k->ep < 0 || k->ed < 0 || k->psize < 0 || (k->psize > 0 && !k->p)) return SCS_NULL;
   dims = (long long)k->z + k->l + k->bsize;
   for (j = 0; j < k->qsize; ++j) dims += k->q[j];
   for (j = 0; j < k->ssize; ++j) dims += ((long long)k->s[j] * (k->s[j] + 1)) / 2;
+  dims += 3LL * ((long long)k->ep + k->ed + k->psize);
   if (dims != m) {
     fprintf(stderr, "scs_b200: cone dims %lld != m %d\n", dims, m);
     return SCS_NULL;
@@ -57,6 +59,7 @@ ScsB200ConeWork *scs_b200_init_cone(const ScsCone *k, scs_int m, const scs_float
   free(bu);
   bl = bu = SCS_NULL;
   if (!c->cones) goto fail;
+  if (b200_cones_set_triples(c->cones, k->ep, k->ed, k->psize, k->p) != 0) goto fail;
   c->d_x = (double *)b200_malloc((size_t)m * 8);
   c->d_ry = (double *)b200_malloc((size_t)m * 8);
   if (!c->d_x || !c->d_ry) goto fail;

@@ -73,6 +73,10 @@ struct B200Cones {
   cusolverDnHandle_t solver;
   cusolverDnParams_t solver_params;
   double *d_scratch;  // m
+  // three-dimensional cones (kernels/cone_triples.cu): ep primal exp, ed dual exp, psize power
+  int n_ep, n_ed, n_pow;
+  long long tri_off;  // first row of the exponential triples
+  double *d_pow;      // power cone parameters (sign = primal / dual), psize
 };
 
 // ------------------------------------------------------------------ SOC kernels
@@ -510,6 +514,7 @@ extern "C" void b200_cones_destroy(B200Cones *c) {
   b200_free(c->d_q_off); b200_free(c->d_small_items); b200_free(c->d_chunks);
   b200_free(c->d_big); b200_free(c->d_chunk_part); b200_free(c->d_head_a0); b200_free(c->d_psd1_off);
   b200_free(c->d_scratch);
+  b200_free(c->d_pow);
   if (c->groups) {
     for (auto &g : *c->groups) {
       b200_free(g.d_off); b200_free(g.d_mats); b200_free(g.d_evals); b200_free(g.d_info);
@@ -523,6 +528,19 @@ extern "C" void b200_cones_destroy(B200Cones *c) {
 }
 
 extern "C" double *b200_cones_scratch(B200Cones *c) { return c->d_scratch; }
+
+// exponential / power cones occupy the LAST 3 (ep + ed + psize) rows (scs.h cone order; the complex
+// PSD cone that would sit between PSD and exp is not supported)
+extern "C" int b200_cones_set_triples(B200Cones *c, int ep, int ed, int psize, const double *h_p) {
+  c->n_ep = ep; c->n_ed = ed; c->n_pow = psize;
+  c->tri_off = (long long)c->m - 3LL * ((long long)ep + ed + psize);
+  if (c->tri_off < 0) return -1;
+  if (psize > 0) {
+    c->d_pow = (double *)b200_malloc((size_t)psize * 8);
+    if (!c->d_pow || b200_h2d(c->d_pow, h_p, (size_t)psize * 8) != 0 || b200_sync() != 0) return -1;
+  }
+  return 0;
+}
 
 extern "C" int b200_cones_project_rest(B200Cones *c, double *d_x, const double *d_s,
                                        const double *d_ry) {
@@ -581,6 +599,11 @@ extern "C" int b200_cones_project_rest(B200Cones *c, double *d_x, const double *
                                                d_ry);
       b200_count_launch(1);
     }
+  }
+  // ---- exponential / power triples
+  if (c->n_ep + c->n_ed + c->n_pow > 0) {
+    if (b200_cone_triples_project(c->n_ep, c->n_ed, c->n_pow, c->tri_off, c->d_pow, d_x, d_s, d_ry) != 0)
+      return -1;
   }
   CUDA_OK(cudaGetLastError());
   return 0;

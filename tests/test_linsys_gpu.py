@@ -132,6 +132,43 @@ def test_spmv_flagged_stream_ragged(lib, reflib, m, n, mean_nnz, seed, grid_cap,
         lib.scs_free_lin_sys_work(w)
 
 
+def test_spmv_full_size_c2_properties(lib):
+    """BASELINE configs[1] size (n=1e6, m=3e6, nnz=1e7): parity of both operators against numpy in fp64,
+    linearity, the adjoint identity <A x, y> = <x, A'y>, and run-to-run bit reproducibility."""
+    rng = np.random.default_rng(1234)
+    n, m = 1_000_000, 3_000_000
+    A = problems.random_sparse_csc(m, n, 10, rng)
+    hp = capi.HostProblem(A, np.zeros(m), np.zeros(n), {"l": m})
+    dr = diag_r_for(n, m, 0)
+    w = lib.scs_init_lin_sys_work(C.byref(hp.A), None, capi.dptr(dr))
+    assert w
+    try:
+        def Ax(x):
+            out = np.zeros(m)
+            assert lib.scs_b200_accum_by_a(w, capi.dptr(x), capi.dptr(out), 0) == 0
+            return out
+
+        def Aty(y):
+            out = np.zeros(n)
+            assert lib.scs_b200_accum_by_atrans(w, capi.dptr(y), capi.dptr(out), 0) == 0
+            return out
+
+        x1, x2 = rng.standard_normal(n), rng.standard_normal(n)
+        y1 = rng.standard_normal(m)
+        ax1, aty1 = Ax(x1), Aty(y1)
+        ref = problems.csc_matvec(A, x1)
+        assert np.abs(ax1 - ref).max() / np.abs(ref).max() <= 1e-13
+        ref = problems.csc_rmatvec(A, y1)
+        assert np.abs(aty1 - ref).max() / np.abs(ref).max() <= 1e-12   # numpy's own cumsum-difference error
+        assert np.array_equal(ax1, Ax(x1)) and np.array_equal(aty1, Aty(y1))      # bit-reproducible
+        lin = Ax(2.0 * x1 - 0.5 * x2) - (2.0 * ax1 - 0.5 * Ax(x2))
+        assert np.abs(lin).max() <= 1e-12 * np.abs(ax1).max()
+        lhs, rhs = float(ax1 @ y1), float(x1 @ aty1)
+        assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), abs(rhs), 1.0)
+    finally:
+        lib.scs_free_lin_sys_work(w)
+
+
 @pytest.mark.parametrize("m,n,col_nnz,z,seed", CASES[:4])
 @pytest.mark.parametrize("warm", [False, True])
 def test_solve_lin_sys_matches_reference(lib, reflib, m, n, col_nnz, z, seed, warm):

@@ -129,6 +129,81 @@ def test_qp_matches_reference(lib, reflib):
     assert np.abs(x - xr).max() <= 1e-4 * max(1.0, np.abs(xr).max())   # strictly convex in x: unique minimiser
 
 
+def exp_pow_problem(seed, n=60):
+    """Strictly feasible primal-dual pair over z x l x SOC x exp(primal, dual) x power(primal, dual):
+    s* in int K, y* in int K*, b = A x* + s*, c = -A'y*  (optimum exists; its value is not known in
+    closed form, the reference is the judge). Cone order: include/scs.h:121-172."""
+    rng = np.random.default_rng(seed)
+    ep, ed = 7, 5
+    pw = [0.3, 0.5, 0.8, -0.25, -0.6]
+    cone = {"z": 6, "l": 20, "q": [4, 9], "ep": ep, "ed": ed, "p": pw}
+    m = capi.cone_rows(cone)
+    A = problems.random_sparse_csc(m, n, 9, rng)
+    s = np.zeros(m)
+    y = rng.uniform(-1, 1, m)                    # zero cone: s = 0, y free
+    o = cone["z"]
+    s[o:o + 20] = rng.uniform(0.5, 1.5, 20); y[o:o + 20] = rng.uniform(0.5, 1.5, 20); o += 20
+    for q in cone["q"]:
+        for v in (s, y):
+            t = rng.standard_normal(q - 1)
+            v[o] = np.linalg.norm(t) + rng.uniform(0.2, 1.0)
+            v[o + 1:o + q] = t
+        o += q
+
+    def exp_primal(v):   # (r, s, t): s > 0, t > s exp(r/s)
+        r, sv = rng.standard_normal(), rng.uniform(0.5, 1.5)
+        v[:] = (r, sv, sv * np.exp(r / sv) + rng.uniform(0.1, 1.0))
+
+    def exp_dual(v):     # (u, v, w): u < 0, e w > -u exp(v/u)
+        u, vv = -rng.uniform(0.5, 1.5), rng.standard_normal()
+        v[:] = (u, vv, -u * np.exp(vv / u) / np.e + rng.uniform(0.1, 1.0))
+
+    for i in range(ep + ed):
+        (exp_primal if i < ep else exp_dual)(s[o:o + 3])
+        (exp_dual if i < ep else exp_primal)(y[o:o + 3])
+        o += 3
+
+    def pow_primal(v, a):   # x^a y^(1-a) > |r|
+        xx, yy = rng.uniform(0.5, 1.5, 2)
+        v[:] = (xx, yy, rng.uniform(-0.5, 0.5) * xx ** a * yy ** (1 - a))
+
+    def pow_dual(v, a):     # (u/a)^a (v/(1-a))^(1-a) > |w|
+        uu, vv = rng.uniform(0.5, 1.5, 2)
+        v[:] = (uu, vv, rng.uniform(-0.5, 0.5) * (uu / a) ** a * (vv / (1 - a)) ** (1 - a))
+
+    for a in pw:
+        if a >= 0:
+            pow_primal(s[o:o + 3], a); pow_dual(y[o:o + 3], a)
+        else:
+            pow_dual(s[o:o + 3], -a); pow_primal(y[o:o + 3], -a)
+        o += 3
+    assert o == m
+    x = rng.uniform(-1, 1, n)
+    b = problems.csc_matvec(A, x) + s
+    c = -problems.csc_rmatvec(A, y)
+    return {"A": A, "b": b, "c": c, "cone": cone, "n": n, "m": m, "opt": None}
+
+
+def test_exp_and_power_cones_match_reference(lib, reflib):
+    """exponential and power cones on the device loop (kernels/cone_triples.cu)."""
+    prob = exp_pow_problem(31)
+    st_m, info_m, x, y, s = solve_with(lib, prob, max_iters=1)
+    st_r, info_r, xr, yr, sr = solve_with(reflib, prob, max_iters=1)
+    assert st_m == st_r and info_m.iter == info_r.iter == 1
+    for a, b, nm in ((x, xr, "x"), (y, yr, "y"), (s, sr, "s")):
+        err = np.abs(a - b).max() / max(1.0, np.abs(b).max())
+        assert err <= 1e-9, (nm, err)
+    eps = 1e-6
+    st_m, info_m, x, y, s = solve_with(lib, prob, eps_abs=eps, eps_rel=eps, max_iters=50000)
+    st_r, info_r, xr, yr, sr = solve_with(reflib, prob, eps_abs=eps, eps_rel=eps, max_iters=50000)
+    print(f"\n[exp/pow] mine it={info_m.iter} pobj={info_m.pobj:.10e} | ref it={info_r.iter} pobj={info_r.pobj:.10e}")
+    assert st_m == st_r == 1
+    assert abs(info_m.pobj - info_r.pobj) <= 100 * eps * max(1.0, abs(info_r.pobj))
+    assert abs(info_m.pobj - info_m.dobj) <= 100 * eps * max(1.0, abs(info_m.pobj))
+    A = prob["A"]
+    assert abs(np.abs(problems.csc_matvec(A, x) + s - prob["b"]).max() - info_m.res_pri) < 1e-10
+
+
 def test_c1_shape_default_settings(lib, reflib):
     """BASELINE configs[0]: n=1000, m=4000, 32 nnz/col SOCP at default eps=1e-4."""
     prob = problems.config("C1")
@@ -170,8 +245,8 @@ def test_max_iters_and_warm_start(lib):
 def test_unsupported_cone_fails_loudly(lib):
     prob = small_problem("lp", seed=1)
     cone = dict(prob["cone"])
-    cone["l"] -= 3
-    cone["ep"] = 1
+    cone["l"] -= 4
+    cone["cs"] = [2]          # complex PSD cone of order 2 = 4 rows: not on the device path
     hp = capi.HostProblem(prob["A"], prob["b"], prob["c"], cone)
     st = capi.default_settings(lib, verbose=0)
     assert not lib.scs_init(C.byref(hp.data), C.byref(hp.cone), C.byref(st))

@@ -340,6 +340,132 @@ k_cg_finish_p2p(int n, double *__restrict__ y, P2pView pv, unsigned long long se
   }
 }
 
+// Two-phase variant for G >= 3 ranks: a reduce-scatter and an all-gather over peer memory instead of
+// every rank reading every partial in full -- 2 (G-1)/G n remote doubles per rank and CG iteration instead
+// of (G-1) n (G = 8: 1.75 n instead of 7 n).
+//   phase 1  rank g sums slice [n g/G, n (g+1)/G) of all partials in rank order into its own `rs` buffer;
+//            the last block to finish publishes "slice ready" (flag slots 8..15) to every rank, itself included;
+//   phase 2  every rank reads the reduced slices of all owners (remote for G-1 of them), applies R_x p (+ P p)
+//            and reduces p'Gp.
+// Every element is summed by exactly one rank in rank order, so all ranks still hold identical bits.
+// `rs` = doubles [2 n, 4 n) of each rank's exchange allocation, double-buffered by seq like the partials.
+__global__ void __launch_bounds__(VEC_THREADS)
+k_cg_finish_p2p2(int n, double *__restrict__ y, P2pView pv, unsigned long long seq, int do_signal,
+                 int y_has_px, const double *__restrict__ rx, const double *__restrict__ x,
+                 int with_dot, B200CgCtl *ctl, const int *skip, double *partials,
+                 unsigned int *counter) {
+  if (skip != nullptr && *skip) return;
+  __shared__ double s_red[64];
+  const int G = pv.nranks, me = pv.rank;
+  const size_t slot = (size_t)(seq & 1ull) * pv.stride;
+  const size_t rs_base = (size_t)2 * pv.stride + slot;
+  if (threadIdx.x == 0) {
+    if (do_signal && blockIdx.x == 0) {
+      __threadfence_system();
+      for (int r = 0; r < G; ++r)
+        if (r != me) *((volatile unsigned long long *)(pv.flags[r] + me)) = seq;
+    }
+    volatile unsigned long long *mine = pv.flags[me];
+    const long long t0 = clock64();
+    for (int r = 0; r < G; ++r) {
+      if (r == me) continue;
+      while (mine[r] < seq) {
+        if (clock64() - t0 > 20000000000LL) { ctl->pad[0] = 1; break; }
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  // ---- phase 1: my slice of the sum
+  {
+    const long long lo = (long long)n * me / G, hi = (long long)n * (me + 1) / G;
+    double *dst = const_cast<double *>(pv.base[me]) + rs_base;
+    constexpr int U = 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < hi; i0 += U * stride) {
+      double sum[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) sum[u] = 0.0;
+      for (int r = 0; r < G; ++r) {  // rank order
+        const double *src = pv.base[r] + slot;
+        double t[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long i = i0 + u * stride;
+          t[u] = (i < hi) ? __ldcg(src + i) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) sum[u] += t[u];
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long i = i0 + u * stride;
+        if (i < hi) dst[i] = sum[u];
+      }
+    }
+  }
+  // the last block to finish its part publishes "slice of step seq ready" to everybody
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned tk = atomicAdd(counter, 1u);
+    if (tk == gridDim.x - 1) {
+      *counter = 0u;  // grid_finish below reuses the ticket counter
+      __threadfence_system();
+      for (int r = 0; r < G; ++r) *((volatile unsigned long long *)(pv.flags[r] + 8 + me)) = seq;
+    }
+    volatile unsigned long long *mine = pv.flags[me] + 8;
+    const long long t0 = clock64();
+    for (int r = 0; r < G; ++r) {
+      while (mine[r] < seq) {
+        if (clock64() - t0 > 20000000000LL) { ctl->pad[0] = 1; break; }
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  // ---- phase 2: gather the reduced slices, finish G p and reduce p'Gp
+  double acc[1] = {0.0};
+  {
+    constexpr int U = 4;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += U * stride) {
+      double t[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * stride;
+        if (i < n) {
+          int owner = (int)(((long long)i * G) / n);  // slice g holds [n g/G, n (g+1)/G)
+          while (owner + 1 < G && (long long)n * (owner + 1) / G <= i) ++owner;
+          while (owner > 0 && (long long)n * owner / G > i) --owner;
+          t[u] = __ldcg(pv.base[owner] + rs_base + i);
+        } else {
+          t[u] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * stride;
+        if (i < n) {
+          const double base = y_has_px ? y[i] + t[u] : t[u];
+          const double xi = x[i];
+          const double out = fma(rx[i], xi, base);
+          y[i] = out;
+          acc[0] = fma(xi, out, acc[0]);
+        }
+      }
+    }
+  }
+  if (!with_dot) return;
+  block_sum<1>(acc, s_red);
+  if (grid_finish<1>(acc, partials, counter, 0u, s_red)) {
+    if (threadIdx.x == 0) {
+      ctl->pGp = acc[0];
+      ctl->alpha = ctl->ztr / acc[0];
+    }
+  }
+}
+
 __global__ void k_add_if_not(int n, double *__restrict__ a, const double *__restrict__ b, const int *skip) {
   if (skip != nullptr && *skip) return;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a[i] += b[i];
@@ -388,6 +514,10 @@ extern "C" int b200_cg_set_preconditioner(const B200Cg *cg, const double *d_Pdia
   return 0;
 }
 
+// peer-memory reduction: 0 = automatic (one pass for 2 ranks, two-phase for more), 1 = one pass, 2 = two-phase
+static int g_p2p_mode = -1;
+extern "C" void scs_b200_set_p2p_mode(int mode) { g_p2p_mode = mode; }
+
 // y = (R_x + P + A' R_y^-1 A) x   (private.c:106-119); dot/hook optional
 static int mat_vec_sharded(B200Cg *cg, const double *d_x, double *d_y, int with_dot,
                            const int *d_skip) {
@@ -426,10 +556,21 @@ static int mat_vec_sharded(B200Cg *cg, const double *d_x, double *d_y, int with_
       pv.flags[r] = r < cg->nranks ? b200_p2p_flags(r) : nullptr;
     }
     if (g > b200_num_sms()) g = b200_num_sms();  // all blocks spin on the flags: keep them co-resident
-    k_cg_finish_p2p<<<g, VEC_THREADS, 0, st>>>(cg->n, d_y, pv, seq, cg->d_p2p_sig == nullptr,
-                                               cg->P != nullptr, cg->d_rx, d_x,
-                                               with_dot, cg->d_ctl, d_skip, cg->d_partials,
-                                               cg->d_counter);
+    // two ranks: one pass (same remote volume, one synchronisation less); more: reduce-scatter + all-gather
+    if (g_p2p_mode < 0) {
+      const char *e = getenv("SCS_B200_P2P_MODE");
+      g_p2p_mode = e ? atoi(e) : 0;
+    }
+    const bool two_phase = g_p2p_mode == 2 || (g_p2p_mode != 1 && cg->nranks >= 3);
+    if (two_phase)
+      k_cg_finish_p2p2<<<g, VEC_THREADS, 0, st>>>(cg->n, d_y, pv, seq, cg->d_p2p_sig == nullptr,
+                                                  cg->P != nullptr, cg->d_rx, d_x, with_dot, cg->d_ctl,
+                                                  d_skip, cg->d_partials, cg->d_counter);
+    else
+      k_cg_finish_p2p<<<g, VEC_THREADS, 0, st>>>(cg->n, d_y, pv, seq, cg->d_p2p_sig == nullptr,
+                                                 cg->P != nullptr, cg->d_rx, d_x,
+                                                 with_dot, cg->d_ctl, d_skip, cg->d_partials,
+                                                 cg->d_counter);
     b200_count_launch(1);
     return 0;
   }

@@ -119,14 +119,15 @@ extern "C" int b200_allgatherv(double *d_buf, const int *offsets) {
 // ---------------------------------------------------------------------------------------------
 // Peer-memory exchange buffers (NVLink P2P through CUDA IPC) for the fused "sum the partial
 // A_g' z over the ranks + R_x p + p'Gp" kernel of the row-sharded CG (kernels/cg.cu). Each rank
-// owns ONE allocation: red[2][n] doubles (double-buffered partials) followed by a flag line
-// per rank; every rank maps the allocation of every other rank. The handles travel in one
+// owns ONE allocation: red[2][n] doubles (double-buffered partials), rs[2][n] doubles (its slice of
+// the reduced vector, two-phase mode) and a line of 64 flags (slots 0..7 "partial ready" per peer,
+// 8..15 "slice ready" per peer); every rank maps the allocation of every other rank. The handles travel in one
 // NCCL all-gather at setup; after that the CG inner loop does not call NCCL at all.
 #define P2P_MAX_RANKS 8
 typedef struct {
   int ok, n;
   double *base[P2P_MAX_RANKS];               // base[r]: rank r's allocation as mapped in THIS process
-  unsigned long long *flags[P2P_MAX_RANKS];  // flags[r] = (unsigned long long*)(base[r] + 2 n)
+  unsigned long long *flags[P2P_MAX_RANKS];  // flags[r] = (unsigned long long*)(base[r] + 4 n)
 } B200P2p;
 static B200P2p g_p2p;
 static ncclResult_t (*N_AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -147,7 +148,7 @@ extern "C" int b200_p2p_setup(int n) {
   if (!N_AllGather) *(void **)(&N_AllGather) = dlsym(N.h, "ncclAllGather");
   if (!N_AllGather) return -1;
   cudaStream_t st = (cudaStream_t)b200_stream();
-  const size_t bytes = ((size_t)2 * n + 64) * 8;
+  const size_t bytes = ((size_t)4 * n + 64) * 8;
   double *mine = (double *)b200_malloc(bytes);
   if (!mine) return -1;
   if (b200_memset0(mine, bytes) != 0) return -1;
@@ -171,7 +172,7 @@ extern "C" int b200_p2p_setup(int n) {
         break;
       }
       g_p2p.base[r] = (double *)p;
-      g_p2p.flags[r] = (unsigned long long *)((double *)p + (size_t)2 * n);
+      g_p2p.flags[r] = (unsigned long long *)((double *)p + (size_t)4 * n);
     }
   }
   b200_free(d_all);

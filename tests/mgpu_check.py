@@ -63,6 +63,28 @@ for name, prob in (
         print(f"[{name}] ranks agree={same} one-iteration err vs reference={err1:.2e} status={st}/{str_} "
               f"iters={info.iter}/{infor.iter} pobj={info.pobj:.9e}/{infor.pobj:.9e} -> {'OK' if good else 'FAIL'}", flush=True)
         ok = ok and good
+# ---- timing of one sharded CG iteration at C2 size, both peer-memory reduction modes (all ranks must call)
+if os.environ.get("MGPU_TIME", "1") != "0":
+    rng = np.random.default_rng(1234)
+    n = 1_000_000
+    m = 3 * n
+    A = problems.random_sparse_csc(m, n, 10, rng)
+    hp = capi.HostProblem(A, np.zeros(m), np.zeros(n), {"l": m})
+    dr = np.empty(n + m + 1)
+    dr[:n] = 1e-6
+    dr[n:] = 10.0
+    w = lib.scs_init_lin_sys_work(C.byref(hp.A), None, capi.dptr(dr))
+    ab = C.c_double()
+    lib.scs_b200_set_p2p_mode.argtypes = [C.c_int]
+    for mode, label in ((1, "one pass: every rank reads every partial"), (2, "two-phase: reduce-scatter + all-gather")):
+        lib.scs_b200_set_p2p_mode(mode)
+        ms = lib.scs_b200_time_cg_iter(w, 30, C.byref(ab))
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(f"[C2 sharded over {world} GPUs] CG iteration, {label}: {float(t[0])*1e3:.1f} us", flush=True)
+    lib.scs_b200_set_p2p_mode(0)
+    lib.scs_free_lin_sys_work(w)
 lib.scs_b200_comm_finalize()
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, src=0)

@@ -31,23 +31,17 @@
 extern "C" {
 #endif
 
-/* primitive types: reference include/scs_types.h (DLONG=0, SFLOAT=0) */
+/* primitive types of the reference build this ABI matches: DLONG=0, SFLOAT=0 (include/scs_types.h) */
 typedef int scs_int;
 typedef double scs_float;
-
 #define SCS_NULL 0
 
-/* exit flags: reference include/scs.h:33-42 */
-#define SCS_INFEASIBLE_INACCURATE (-7)
-#define SCS_UNBOUNDED_INACCURATE (-6)
-#define SCS_SIGINT (-5)
-#define SCS_FAILED (-4)
-#define SCS_INDETERMINATE (-3)
-#define SCS_INFEASIBLE (-2)
-#define SCS_UNBOUNDED (-1)
-#define SCS_UNFINISHED (0)
-#define SCS_SOLVED (1)
-#define SCS_SOLVED_INACCURATE (2)
+/* exit flags of scs_solve / scs (values of reference include/scs.h:33-42) */
+enum {
+  SCS_INFEASIBLE_INACCURATE = -7, SCS_UNBOUNDED_INACCURATE = -6, SCS_SIGINT = -5, SCS_FAILED = -4,
+  SCS_INDETERMINATE = -3, SCS_INFEASIBLE = -2, SCS_UNBOUNDED = -1, SCS_UNFINISHED = 0, SCS_SOLVED = 1,
+  SCS_SOLVED_INACCURATE = 2
+};
 
 /* opaque workspaces */
 typedef struct SCS_WORK ScsWork;
@@ -55,113 +49,79 @@ typedef struct SCS_LIN_SYS_WORK ScsLinSysWork;
 typedef struct SCS_B200_CONE_WORK ScsB200ConeWork;
 typedef struct SCS_B200_AA_WORK ScsB200AaWork;
 
-/* CSC sparse matrix, zero-based (reference include/scs.h:47-58). */
+/* The data structs below declare their members in the reference's order and with the reference's types,
+ * several per line: the LAYOUT (pinned by tests/test_abi_cpu.py: sizes and offsets) is what a caller compiled
+ * against the reference's headers relies on. */
+
+/* CSC sparse matrix, zero-based (layout of reference include/scs.h:47-58): values x[nnz], row indices i[nnz],
+ * column pointers p[n+1], then the shape m x n */
 typedef struct {
-  scs_float *x; /* values, nnz */
-  scs_int *i;   /* row indices, nnz */
-  scs_int *p;   /* column pointers, n+1 */
-  scs_int m;    /* rows */
-  scs_int n;    /* cols */
+  scs_float *x;
+  scs_int *i, *p;
+  scs_int m, n;
 } ScsMatrix;
 
-/* solver settings (reference include/scs.h:61-101; defaults glbopts.h:35-50) */
+/* solver settings (layout of reference include/scs.h:61-101; defaults glbopts.h:35-50) */
 typedef struct {
   scs_int normalize;
   scs_float scale;
   scs_int adaptive_scale;
   scs_float rho_x;
   scs_int max_iters;
-  scs_float eps_abs;
-  scs_float eps_rel;
-  scs_float eps_infeas;
-  scs_float alpha;
-  scs_float time_limit_secs;
-  scs_int verbose;
-  scs_int warm_start;
-  scs_int acceleration_lookback;
-  scs_int acceleration_interval;
-  scs_int acceleration_type_1;
-  scs_float acceleration_regularization;
-  scs_float acceleration_relaxation;
-  const char *write_data_filename;
-  const char *log_csv_filename;
+  scs_float eps_abs, eps_rel, eps_infeas, alpha, time_limit_secs;
+  scs_int verbose, warm_start;
+  scs_int acceleration_lookback, acceleration_interval, acceleration_type_1;
+  scs_float acceleration_regularization, acceleration_relaxation;
+  const char *write_data_filename, *log_csv_filename; /* accepted, ignored with a warning */
 } ScsSettings;
 
-/* problem data (reference include/scs.h:104-119) */
+/* problem data (layout of reference include/scs.h:104-119): A is m x n, P the n x n upper triangle or NULL */
 typedef struct {
-  scs_int m;
-  scs_int n;
-  ScsMatrix *A; /* m x n */
-  ScsMatrix *P; /* n x n upper triangle, or NULL */
-  scs_float *b; /* m */
-  scs_float *c; /* n */
+  scs_int m, n;
+  ScsMatrix *A, *P;
+  scs_float *b, *c; /* lengths m, n */
 } ScsData;
 
-/* cone product K, rows of A in this order (reference include/scs.h:122-172) */
+/* cone product K; the rows of A follow this order (layout of reference include/scs.h:122-172) */
 typedef struct {
-  scs_int z;      /* zero cone rows */
-  scs_int l;      /* nonnegative orthant rows */
-  scs_float *bu;  /* box upper, bsize-1 */
-  scs_float *bl;  /* box lower, bsize-1 */
-  scs_int bsize;  /* box cone total length (incl. t) */
-  scs_int *q;     /* second-order cone sizes */
+  scs_int z, l;        /* zero-cone rows, nonnegative-orthant rows */
+  scs_float *bu, *bl;  /* box cone bounds, bsize-1 each */
+  scs_int bsize;       /* box cone length including t */
+  scs_int *q;          /* second-order cone sizes [qsize] */
   scs_int qsize;
-  scs_int *s;     /* PSD cone matrix orders */
+  scs_int *s;          /* PSD matrix orders [ssize] */
   scs_int ssize;
-  scs_int *cs;    /* complex PSD orders  (not supported by the device path) */
+  scs_int *cs;         /* complex PSD orders [cssize]: NOT supported by the device path */
   scs_int cssize;
-  scs_int ep;     /* primal exp triples  (not supported by the device path) */
-  scs_int ed;     /* dual exp triples    (not supported by the device path) */
-  scs_float *p;   /* power cone params   (not supported by the device path) */
+  scs_int ep, ed;      /* primal / dual exponential triples */
+  scs_float *p;        /* power cone parameters in [-1, 1] [psize]; negative = dual cone */
   scs_int psize;
 } ScsCone;
 
-/* solution / certificate (reference include/scs.h:180-187) */
+/* solution or certificate (layout of reference include/scs.h:180-187) */
 typedef struct {
-  scs_float *x;
-  scs_float *y;
-  scs_float *s;
+  scs_float *x, *y, *s;
 } ScsSolution;
 
-/* AA lifetime counters (reference include/aa_stats.h:21-42) */
+/* Anderson-acceleration lifetime counters (layout of reference include/aa_stats.h:21-42) */
 typedef struct {
-  scs_int iter;
-  scs_int n_accept;
-  scs_int n_reject_lapack;
-  scs_int n_reject_rank0;
-  scs_int n_reject_nonfinite;
-  scs_int n_reject_weight_cap;
-  scs_int n_safeguard_reject;
+  scs_int iter, n_accept;
+  scs_int n_reject_lapack, n_reject_rank0, n_reject_nonfinite, n_reject_weight_cap, n_safeguard_reject;
   scs_int last_rank;
-  scs_float last_aa_norm;
-  scs_float last_regularization;
+  scs_float last_aa_norm, last_regularization;
 } AaStats;
 
-/* solve report; times in milliseconds (reference include/scs.h:190-244) */
+/* solve report; times in milliseconds (layout of reference include/scs.h:190-244) */
 typedef struct {
   scs_int iter;
-  char status[128];
-  char lin_sys_solver[128];
-  scs_int status_val;
-  scs_int scale_updates;
-  scs_float pobj;
-  scs_float dobj;
-  scs_float res_pri;
-  scs_float res_dual;
-  scs_float gap;
-  scs_float res_infeas;
-  scs_float res_unbdd_a;
-  scs_float res_unbdd_p;
-  scs_float setup_time;
-  scs_float solve_time;
-  scs_float scale;
-  scs_float comp_slack;
-  scs_int rejected_accel_steps;
-  scs_int accepted_accel_steps;
+  char status[128], lin_sys_solver[128];
+  scs_int status_val, scale_updates;
+  scs_float pobj, dobj, res_pri, res_dual, gap;
+  scs_float res_infeas, res_unbdd_a, res_unbdd_p;
+  scs_float setup_time, solve_time, scale, comp_slack;
+  scs_int rejected_accel_steps, accepted_accel_steps;
   AaStats aa_stats;
-  scs_float lin_sys_time;
-  scs_float cone_time;
-  scs_float accel_time;
+  scs_float lin_sys_time, cone_time, accel_time;
 } ScsInfo;
 
 /* ------------------------------------------------------------------ (1) --
@@ -220,7 +180,7 @@ double scs_b200_time_spmv(ScsLinSysWork *w, scs_int op, scs_int reps,
 double scs_b200_time_cg_iter(ScsLinSysWork *w, scs_int reps, double *alg_bytes);
 
 /* Cone operator: replaces reference src/cones.c:1498-1596 (init_cone /
- * proj_dual_cone / finish_cone) for zero, LP, box, SOC and PSD cones.
+ * proj_dual_cone / finish_cone) for zero, LP, box, SOC, PSD, exponential and power cones.
  * D is the row scaling of the equilibrated problem (length m) or NULL
  * (reference normalize_box_cone, cones.c:1160-1177).  x (length m) and r_y
  * (length m or NULL) are HOST arrays; x is projected in place onto the dual
@@ -267,6 +227,8 @@ scs_int scs_b200_set_max_iters(ScsWork *w, scs_int max_iters);
 scs_int scs_b200_comm_unique_id(char *out128);
 scs_int scs_b200_comm_init(scs_int rank, scs_int nranks, const char *id128);
 scs_int scs_b200_comm_finalize(void);
+/* peer-memory reduction of the sharded CG: 0 automatic, 1 one pass, 2 reduce-scatter + all-gather */
+void scs_b200_set_p2p_mode(int mode);
 /* contiguous row blocks of A balanced by nonzeros: offsets[nranks+1] (host logic, no GPU needed) */
 scs_int scs_b200_row_partition(scs_int m, scs_int n, const scs_int *Ap, const scs_int *Ai,
                                scs_int nranks, scs_int *offsets);

@@ -72,7 +72,7 @@ typedef struct {
   scs_int verbose, warm_start;
   scs_int acceleration_lookback, acceleration_interval, acceleration_type_1;
   scs_float acceleration_regularization, acceleration_relaxation;
-  const char *write_data_filename, *log_csv_filename; /* accepted, ignored with a warning */
+  const char *write_data_filename, *log_csv_filename; /* the CSV log is accepted and ignored with a warning */
 } ScsSettings;
 
 /* problem data (layout of reference include/scs.h:104-119): A is m x n, P the n x n upper triangle or NULL */
@@ -232,6 +232,14 @@ void scs_b200_set_p2p_mode(int mode);
 /* contiguous row blocks of A balanced by nonzeros: offsets[nranks+1] (host logic, no GPU needed) */
 scs_int scs_b200_row_partition(scs_int m, scs_int n, const scs_int *Ap, const scs_int *Ai,
                                scs_int nranks, scs_int *offsets);
+
+/* The SCS problem-file format (replaces reference src/rw.c:574-684 SCS(write_data) / SCS(read_data)): files
+ * written by either library are read by the other. scs_init honours ScsSettings.write_data_filename with it.
+ * read: allocates *d, *k, *stgs (release with scs_b200_free_data); returns 0, or -1 with everything freed. */
+scs_int scs_b200_write_data(const char *filename, const ScsData *d, const ScsCone *k,
+                            const ScsSettings *stgs);
+scs_int scs_b200_read_data(const char *filename, ScsData **d, ScsCone **k, ScsSettings **stgs);
+void scs_b200_free_data(ScsData *d, ScsCone *k, ScsSettings *stgs);
 
 /* Number of kernels this library has launched in this process. */
 long long scs_b200_launch_count(void);

@@ -341,7 +341,10 @@ ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {
     printf("ERROR: scs_b200 needs an sm_100 (B200) CUDA device: %s\n", b200_last_error());
     return SCS_NULL;
   }
-  if (stgs->write_data_filename) printf("WARN: write_data_filename is not supported by scs_b200; ignored\n");
+  if (stgs->write_data_filename) { /* reference scs.c:1270-1273 */
+    printf("Writing raw problem data to %s\n", stgs->write_data_filename);
+    scs_b200_write_data(stgs->write_data_filename, d, k, stgs);
+  }
   if (stgs->log_csv_filename) printf("WARN: log_csv_filename is not supported by scs_b200; ignored\n");
   w = (ScsWork *)calloc(1, sizeof(ScsWork));
   if (!w) return SCS_NULL;

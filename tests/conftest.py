@@ -15,6 +15,8 @@ ORACLE_LIB = os.path.join(ROOT, "oracle", "liboracle.so")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    config.addinivalue_line("markers", "gpu_unverified: needs a real B200 and has NOT been run on one yet (written after the "
+                            "round's GPU budget was spent); promote to `gpu` after the first green run: -m gpu_unverified")
 
 
 @pytest.fixture(scope="session")

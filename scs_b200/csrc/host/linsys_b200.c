@@ -13,9 +13,11 @@
  * ADMM driver (host/scs_driver.c) so that the hot loop never crosses PCIe.
  */
 #include "linsys_b200.h"
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 const char *scs_get_lin_sys_method(void) { return "sparse-indirect-b200-cuda"; }
 
@@ -23,32 +25,128 @@ const char *scs_get_lin_sys_method(void) { return "sparse-indirect-b200-cuda"; }
  * (= CSR of the original). Entries of each output column keep ascending source
  * column order, exactly like reference private.c:7-46, so that the per-row
  * summation order of A x matches the reference's accum_by_atrans(At, ...). */
-static int transpose_csc(int m, int n, const int *Ap, const int *Ai, const double *Ax, int **Cp_out,
-                         int **Ci_out, double **Cx_out) {
+/* Host threads for the setup-time passes over nnz (transpose here, the SpMV plan in kernels/spmv.cu):
+ * SCS_B200_HOST_THREADS, else min(16, online CPUs); 1 for small inputs. */
+int b200_host_threads(long long work_items) {
+  const char *e = getenv("SCS_B200_HOST_THREADS");
+  long t = e ? atol(e) : sysconf(_SC_NPROCESSORS_ONLN);
+  if (!e && t > 16) t = 16;
+  if (!e && work_items < 500000) t = 1;
+  if (t < 1) t = 1;
+  if (t > 64) t = 64;
+  return (int)t;
+}
+
+/* The transpose is a stable counting sort. Parallel version: the OUTPUT rows are split into T contiguous
+ * ranges; every thread scans the whole input in column order and handles only the entries whose row falls
+ * in its range, so writes never collide, no atomics are needed and the result is identical to the serial
+ * loop (entries of an output row keep ascending source-column order). The extra cost is T sequential reads
+ * of the index array, which is cheap next to the random writes that dominate the serial version. */
+typedef struct {
+  int m, n, r0, r1;
+  const int *Ap, *Ai;
+  const double *Ax;
+  int *cursor, *Ci;
+  double *Cx;
+  int phase; /* 0: count, 1: fill */
+} TrJob;
+
+static void *tr_worker(void *arg) {
+  TrJob *jb = (TrJob *)arg;
+  const int r0 = jb->r0, r1 = jb->r1;
+  const int *Ai = jb->Ai;
+  if (jb->phase == 0) {
+    /* count: this thread's SLICE OF THE INPUT [r0, r1) (entry indices), relaxed atomic increments --
+     * integer counts do not depend on the order, so the result is still deterministic */
+    long long k;
+    int *cnt = jb->cursor;
+    for (k = r0; k < r1; ++k) __atomic_fetch_add(&cnt[Ai[k]], 1, __ATOMIC_RELAXED);
+  } else {
+    int j, k;
+    int *z = jb->cursor;
+    for (j = 0; j < jb->n; ++j) {
+      for (k = jb->Ap[j]; k < jb->Ap[j + 1]; ++k) {
+        const int r = Ai[k];
+        if (r >= r0 && r < r1) {
+          const int q = z[r]++;
+          jb->Ci[q] = j;
+          jb->Cx[q] = jb->Ax[k];
+        }
+      }
+    }
+  }
+  return NULL;
+}
+
+static void tr_run(TrJob *jobs, int T) {
+  pthread_t th[64];
+  int t, started = 0;
+  for (t = 1; t < T; ++t) {
+    if (pthread_create(&th[t], NULL, tr_worker, &jobs[t]) != 0) break;
+    started = t;
+  }
+  tr_worker(&jobs[0]);
+  for (t = started + 1; t < T; ++t) tr_worker(&jobs[t]); /* threads that could not be created: run inline */
+  for (t = 1; t <= started; ++t) pthread_join(th[t], NULL);
+}
+
+int scs_b200_transpose_csc(int m, int n, const int *Ap, const int *Ai, const double *Ax, int **Cp_out,
+                           int **Ci_out, double **Cx_out) {
   const int nnz = Ap[n];
   int *Cp = (int *)calloc((size_t)m + 1, sizeof(int));
   int *Ci = (int *)malloc(((size_t)nnz + 1) * sizeof(int));
   double *Cx = (double *)malloc(((size_t)nnz + 1) * sizeof(double));
   int *z = (int *)calloc((size_t)m + 1, sizeof(int));
-  int i, j, k;
+  TrJob jobs[64];
+  int i, t;
+  int T = b200_host_threads(nnz);
+  if (T > m) T = m > 0 ? m : 1;
   if (!Cp || !Ci || !Cx || !z) {
     free(Cp); free(Ci); free(Cx); free(z);
     return -1;
   }
-  for (k = 0; k < nnz; ++k) z[Ai[k]]++;
+  for (t = 0; t < T; ++t) {
+    jobs[t].m = m; jobs[t].n = n; jobs[t].Ap = Ap; jobs[t].Ai = Ai; jobs[t].Ax = Ax;
+    jobs[t].cursor = z; jobs[t].Ci = Ci; jobs[t].Cx = Cx;
+  }
+  /* count: equal slices of the input entries */
+  for (t = 0; t < T; ++t) {
+    jobs[t].phase = 0;
+    jobs[t].r0 = (int)((long long)nnz * t / T);
+    jobs[t].r1 = (int)((long long)nnz * (t + 1) / T);
+  }
+  tr_run(jobs, T);
   Cp[0] = 0;
   for (i = 0; i < m; ++i) Cp[i + 1] = Cp[i] + z[i];
   for (i = 0; i < m; ++i) z[i] = Cp[i];
-  for (j = 0; j < n; ++j) {
-    for (k = Ap[j]; k < Ap[j + 1]; ++k) {
-      const int q = z[Ai[k]]++;
-      Ci[q] = j;
-      Cx[q] = Ax[k];
+  /* fill: row ranges balanced by their number of entries */
+  {
+    int r = 0;
+    for (t = 0; t < T; ++t) {
+      const long long target = (long long)nnz * (t + 1) / T;
+      jobs[t].phase = 1;
+      jobs[t].r0 = r;
+      if (t == T - 1) {
+        r = m;
+      } else {
+        int lo = r, hi = m; /* first row index whose prefix reaches the target */
+        while (lo < hi) {
+          const int mid = lo + (hi - lo) / 2;
+          if (Cp[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        r = lo;
+      }
+      jobs[t].r1 = r;
     }
   }
+  tr_run(jobs, T);
   free(z);
   *Cp_out = Cp; *Ci_out = Ci; *Cx_out = Cx;
   return 0;
+}
+static int transpose_csc(int m, int n, const int *Ap, const int *Ai, const double *Ax, int **Cp_out,
+                         int **Ci_out, double **Cx_out) {
+  return scs_b200_transpose_csc(m, n, Ap, Ai, Ax, Cp_out, Ci_out, Cx_out);
 }
 
 /* expand upper-triangular CSC P into the full symmetric matrix in CSR

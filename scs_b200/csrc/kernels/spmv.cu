@@ -31,7 +31,11 @@
 #include "../dev_api.h"
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
+#include <thread>
 #include <vector>
+
+extern "C" int b200_host_threads(long long work_items);  // host/linsys_b200.c
 
 // tuning knobs (overridable with -D for sweeps; see profiles/README.md for the measurements)
 #ifndef SPMV_DEFAULT_VERSION
@@ -830,8 +834,15 @@ spmv_flag_kernel(const int *__restrict__ colidx, const double *__restrict__ vals
 // re-executes the kernel's lane algorithm on this plan in numpy).
 struct Spmv3Plan {
   std::vector<int> rowptr;   // stored row pointers (every row has >= 1 stored entry)
-  std::vector<int> idx;      // column | END | SKIP
-  std::vector<double> vals;
+  // column | END | SKIP and the values: raw buffers, deliberately NOT value-initialised (a 120 MB memset per
+  // operator at C2) -- every element is written by the fill below
+  struct Raw {
+    void *p = nullptr;
+    ~Raw() { free(p); }
+  } idx_mem, vals_mem;
+  size_t stored_count = 0;
+  int *idx_data() const { return static_cast<int *>(idx_mem.p); }
+  double *vals_data() const { return static_cast<double *>(vals_mem.p); }
   std::vector<int4> wt;      // padded per CTA to a multiple of SPMV3_NCW: {row0, k0, cnt, nrows}
   std::vector<int> cta_begin;  // grid+1, in groups of SPMV3_NCW descriptors
   int grid = 0;
@@ -851,26 +862,65 @@ static bool spmv3_build_plan(int nrows, int ncols, const int *rp, const int *ci,
   const long long stored = nnz + empties;
   if (stored > 2000000000LL) return false;
   P.rowptr.resize((size_t)nrows + 1);
-  P.idx.resize((size_t)stored);
-  P.vals.resize((size_t)stored);
-  int pos = 0;
-  for (int r = 0; r < nrows; ++r) {
-    P.rowptr[r] = pos;
-    const int a = rp[r], b = rp[r + 1];
-    if (a == b) {
-      P.idx[pos] = (int)(SPMV3_END | SPMV3_SKIP);
-      P.vals[pos] = 0.0;
-      ++pos;
-    } else {
-      for (int k = a; k < b; ++k) {
-        P.idx[pos] = ci[k];
-        P.vals[pos] = va[k];
-        ++pos;
+  P.stored_count = (size_t)stored;
+  P.idx_mem.p = malloc(((size_t)stored + 1) * sizeof(int));
+  P.vals_mem.p = malloc(((size_t)stored + 1) * sizeof(double));
+  if (!P.idx_mem.p || !P.vals_mem.p) return false;
+  {
+    int pos = 0;
+    for (int r = 0; r < nrows; ++r) {
+      P.rowptr[r] = pos;
+      const int len = rp[r + 1] - rp[r];
+      pos += len > 0 ? len : 1;
+    }
+    P.rowptr[nrows] = pos;
+  }
+  // copy + flag the entries, rows split over host threads (disjoint output ranges)
+  {
+    int *out_i = P.idx_data();
+    double *out_v = P.vals_data();
+    const int *orp = P.rowptr.data();
+    auto fill = [=](int ra, int rb) {
+      for (int r = ra; r < rb; ++r) {
+        const int a = rp[r], b = rp[r + 1];
+        int pos = orp[r];
+        if (a == b) {
+          out_i[pos] = (int)(SPMV3_END | SPMV3_SKIP);
+          out_v[pos] = 0.0;
+        } else {
+          for (int k = a; k < b; ++k, ++pos) {
+            out_i[pos] = ci[k];
+            out_v[pos] = va[k];
+          }
+          out_i[pos - 1] = (int)((unsigned)out_i[pos - 1] | SPMV3_END);
+        }
       }
-      P.idx[pos - 1] = (int)((unsigned)P.idx[pos - 1] | SPMV3_END);
+    };
+    const int T = b200_host_threads(stored);
+    if (T <= 1) {
+      fill(0, nrows);
+    } else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < T; ++t) {
+        // ranges balanced by stored entries
+        auto cut = [&](int q) {
+          const long long target = stored * q / T;
+          return (int)(std::lower_bound(P.rowptr.begin(), P.rowptr.end(), (int)target) - P.rowptr.begin());
+        };
+        int ra = t == 0 ? 0 : cut(t), rb = t == T - 1 ? nrows : cut(t + 1);
+        if (ra > nrows) ra = nrows;
+        if (rb > nrows) rb = nrows;
+        if (rb > ra) {
+          try {
+            th.emplace_back(fill, ra, rb);
+          } catch (...) {  // no more threads available: do this range here
+            fill(ra, rb);
+          }
+        }
+      }
+      for (auto &x : th) x.join();
     }
   }
-  P.rowptr[nrows] = pos;
   // warp-tiles: whole rows, aligned span (k0 & ~3 .. end) <= 128 entries
   std::vector<int4> real;
   real.reserve((size_t)(stored / 100 + 16));
@@ -927,7 +977,7 @@ extern "C" B200Spmv3PlanHost *b200_spmv3_plan_build(int nrows, int ncols, const 
 extern "C" void b200_spmv3_plan_free(B200Spmv3PlanHost *h) { delete h; }
 extern "C" int b200_spmv3_plan_info(const B200Spmv3PlanHost *h, int *stored, int *nwt, int *ndesc, int *grid,
                                     int *ncw) {
-  *stored = (int)h->plan.idx.size();
+  *stored = (int)h->plan.stored_count;
   *nwt = h->plan.nwt;
   *ndesc = (int)h->plan.wt.size();
   *grid = h->plan.grid;
@@ -935,8 +985,8 @@ extern "C" int b200_spmv3_plan_info(const B200Spmv3PlanHost *h, int *stored, int
   return 0;
 }
 extern "C" const int *b200_spmv3_plan_rowptr(const B200Spmv3PlanHost *h) { return h->plan.rowptr.data(); }
-extern "C" const int *b200_spmv3_plan_idx(const B200Spmv3PlanHost *h) { return h->plan.idx.data(); }
-extern "C" const double *b200_spmv3_plan_vals(const B200Spmv3PlanHost *h) { return h->plan.vals.data(); }
+extern "C" const int *b200_spmv3_plan_idx(const B200Spmv3PlanHost *h) { return h->plan.idx_data(); }
+extern "C" const double *b200_spmv3_plan_vals(const B200Spmv3PlanHost *h) { return h->plan.vals_data(); }
 extern "C" const int *b200_spmv3_plan_desc(const B200Spmv3PlanHost *h) {
   return reinterpret_cast<const int *>(h->plan.wt.data());
 }
@@ -970,7 +1020,7 @@ static void spmv_set_attrs() {
 // v3: upload the flagged stream (it IS the operator's CSR: rowptr / colidx / vals stay a valid CSR with
 // explicit zeros, flags in the two top bits of colidx) plus the warp-tile descriptors
 static int spmv_upload_v3(B200Spmv *M, const Spmv3Plan &P) {
-  const size_t stored = P.idx.size();
+  const size_t stored = P.stored_count;
   const size_t pad = ((stored + 3) & ~(size_t)3) + 8;
   M->stored = (long long)stored;
   M->grid = P.grid;
@@ -992,8 +1042,8 @@ static int spmv_upload_v3(B200Spmv *M, const Spmv3Plan &P) {
   rc |= b200_memset0(M->d_vals, pad * 8);
   rc |= b200_memset0(M->d_counter, 64);
   rc |= b200_h2d(M->d_rowptr, P.rowptr.data(), (size_t)(M->nrows + 1) * 4);
-  rc |= b200_h2d(M->d_colidx, P.idx.data(), stored * 4);
-  rc |= b200_h2d(M->d_vals, P.vals.data(), stored * 8);
+  rc |= b200_h2d(M->d_colidx, P.idx_data(), stored * 4);
+  rc |= b200_h2d(M->d_vals, P.vals_data(), stored * 8);
   rc |= b200_h2d(M->d_wt3, P.wt.data(), P.wt.size() * sizeof(int4));
   rc |= b200_h2d(M->d_cta_begin3, P.cta_begin.data(), P.cta_begin.size() * 4);
   rc |= b200_sync();  // the plan's host vectors go out of scope

@@ -70,3 +70,22 @@ def test_power_cone_host_restatement_matches_reference():
         host.b200_triples_host_pow(capi.dptr(a), float(pw[i]))
         worst = max(worst, np.abs(a - ref_proj[i]).max() / max(1.0, np.abs(x[i]).max()))
     assert worst <= 1e-12, worst
+
+
+def test_host_restatement_matches_committed_goldens():
+    """same check against tests/golden/cone_triples.npz (generated from the reference by
+    oracle/make_golden_triples.py), so it also runs where oracle/_ref is absent"""
+    host = C.CDLL(HOST_LIB)
+    host.b200_triples_host_exp.argtypes = [capi.c_double_p, C.c_int]
+    host.b200_triples_host_pow.argtypes = [capi.c_double_p, C.c_double]
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cone_triples.npz"))
+    x = g["x"]
+    for primal, key in ((1, "exp_primal"), (0, "exp_dual")):
+        for i in range(len(x)):
+            a = x[i].copy()
+            host.b200_triples_host_exp(capi.dptr(a), primal)
+            assert np.abs(a - g[key][i]).max() <= 1e-13 * max(1.0, np.abs(x[i]).max()), (key, i)
+    for i in range(len(x)):
+        a = x[i].copy()
+        host.b200_triples_host_pow(capi.dptr(a), float(g["pow_params"][i]))
+        assert np.abs(a - g["pow_proj"][i]).max() <= 1e-12 * max(1.0, np.abs(x[i]).max()), i

@@ -69,3 +69,25 @@ def test_reference_fixture_known_optimum(lib, name):
         assert abs(perr) < 1e-4 and abs(derr) < 1e-4
     finally:
         lib.scs_b200_free_data(d, k, s)
+
+
+def test_exp_power_operator_matches_committed_goldens(lib):
+    """device exp / power cone kernels under the Moreau wrapper against tests/golden/cone_triples.npz
+    (reference outputs); tolerances as in tests/test_cones_gpu.py (1e-8 max with power cones)."""
+    if not lib.scs_b200_device_ok():
+        pytest.skip("no sm_100 device")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cone_triples.npz"))
+    cone = {"l": 3, "ep": int(g["mixed_ep"]), "ed": int(g["mixed_ed"]), "p": list(g["mixed_p"])}
+    m = capi.cone_rows(cone)
+    k, keep = capi.make_cone(cone)
+    cw = lib.scs_b200_init_cone(C.byref(k), m, None)
+    assert cw
+    try:
+        for tag, ry in (("id", None), ("ry", g["mixed_ry"].copy())):
+            out = g["mixed_x"].copy()
+            assert lib.scs_b200_proj_dual_cone(cw, capi.dptr(out), capi.dptr(ry)) == 0
+            ref = g[f"mixed_out_{tag}"]
+            err = np.abs(out - ref) / max(np.abs(ref).max(), 1.0)
+            assert err.max() <= 1e-8 and np.median(err) <= 1e-14, (tag, err.max())
+    finally:
+        lib.scs_b200_finish_cone(cw)

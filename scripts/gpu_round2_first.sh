@@ -1,0 +1,17 @@
+#!/bin/bash
+# First GPU call of the next round (one GPU, ~6 min): (1) the tests staged as `gpu_unverified` at the end of round 1
+# (reference fixtures through the device driver, exp/power goldens), (2) e2e / value with the threaded host setup,
+# (3) the full gated suite. Everything -> gpurun_out/round2_first.log
+mkdir -p gpurun_out
+L=gpurun_out/round2_first.log
+: > $L
+echo "=== staged tests (-m gpu_unverified)" >> $L
+timeout 600 python -m pytest tests -q -m gpu_unverified -s 2>&1 | tail -25 >> $L
+echo "=== bench (no cpu baseline)" >> $L
+timeout 600 python bench.py --steps 100 --warmup 5 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.readline())
+print({k:d[k] for k in ('value','ms_per_step','cg_iters_per_step','gpu_launches','lin_sys_ms','setup_ms')}, 'e2e', d['e2e']['value'], 'frac', d['roofline']['frac'])" >> $L
+echo "=== full gated suite" >> $L
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -5 >> $L
+cat $L

@@ -1,4 +1,4 @@
-"""GPU parity of the cone operator (zero / LP / box / SOC / PSD under the Moreau
+"""GPU parity of the cone operator (zero / LP / box / SOC / PSD / exponential / power under the Moreau
 wrapper) against the reference's own _scs_proj_dual_cone (src/cones.c:1552-1596)
 from oracle/_ref, on identical inputs. Tolerance: 1e-13 relative."""
 import ctypes as C

@@ -271,3 +271,27 @@ def test_parallel_transpose_matches_scipy(lib, threads, shape, monkeypatch):
     R = sp.csc_matrix((data, idx, ptr), shape=(m, n)).tocsr()
     R.sort_indices()
     assert np.array_equal(got_p, R.indptr) and np.array_equal(got_i, R.indices) and np.array_equal(got_x, R.data)
+
+
+def test_plan_property_random_shapes(lib):
+    """hypothesis: arbitrary row-length patterns (runs of empty rows, rows of exactly 124 entries, single
+    rows, tiny column spaces) -> plan invariants hold and the lane algorithm reproduces the CSR product"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.one_of(st.integers(0, 6), st.sampled_from([0, 1, 2, 123, MAXROW])), min_size=1, max_size=400),
+           st.integers(1, 7), st.integers(0, 2**31 - 1))
+    def check(lens, grid_cap, seed):
+        rng = np.random.default_rng(seed)
+        ncols = max(MAXROW, 130)
+        lens_a = np.asarray(lens)
+        rp, ci, va = random_csr(len(lens), ncols, rng, lens_a)
+        plan = build_plan(lib, len(lens), ncols, rp, ci, va, grid_cap)
+        assert plan is not None
+        check_invariants(plan, len(lens), rp, ci, va)
+        x = rng.standard_normal(ncols)
+        y = emulate_kernel(plan, len(lens), x, rng)
+        ref = np.array([np.dot(va[rp[r]:rp[r + 1]], x[ci[rp[r]:rp[r + 1]]]) for r in range(len(lens))])
+        assert np.abs(y - ref).max() <= 1e-13 * (np.abs(ref).max() + 1.0)
+
+    check()

@@ -311,8 +311,8 @@ static void print_header(const ScsWork *w) {
   printf("\n\t       SCS hot path on B200 (scs_b200 %s, API of SCS 3.2.11)\n", SCS_VERSION_STR);
   for (i = 0; i < 78; ++i) printf("-");
   printf("\nproblem:  variables n: %i, constraints m: %i\n", w->n, w->m);
-  printf("cones: \t  z: %i, l: %i, b: %i, q: %i cones, s: %i cones\n", k->z, k->l, k->bsize, k->qsize,
-         k->ssize);
+  printf("cones: \t  z: %i, l: %i, b: %i, q: %i cones, s: %i cones, exp: %i + %i dual, pow: %i\n", k->z, k->l,
+         k->bsize, k->qsize, k->ssize, k->ep, k->ed, k->psize);
   printf("settings: eps_abs: %.1e, eps_rel: %.1e, eps_infeas: %.1e\n\t  alpha: %.2f, scale: %.2e, "
          "adaptive_scale: %i\n\t  max_iters: %i, normalize: %i, rho_x: %.2e\n",
          w->stgs->eps_abs, w->stgs->eps_rel, w->stgs->eps_infeas, w->stgs->alpha, w->stgs->scale,

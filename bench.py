@@ -237,6 +237,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not os.path.exists(os.path.join(ROOT, "scs_b200", "libscs_b200.so")) and rank == 0 and world == 1:
+        import __graft_entry__
+        __graft_entry__.build()  # fresh checkout: the built library is git-ignored
     from scs_b200 import capi
 
     base = {"metric": "ADMM iters/sec", "unit": "iters/s", "n_gpus": world, "steps": args.steps,

@@ -163,6 +163,7 @@ def cone_rows(cone):
     bs = (len(cone["bu"]) + 1) if cone.get("bu") is not None and len(cone["bu"]) else int(cone.get("bsize", 0))
     return (int(cone.get("z", 0)) + int(cone.get("l", 0)) + bs + int(sum(q)) +
             int(sum(int(k) * (int(k) + 1) // 2 for k in s)) +
+            int(sum(int(k) * int(k) for k in (cone.get("cs", []) or []))) +
             3 * (int(cone.get("ep", 0)) + int(cone.get("ed", 0)) + len(cone.get("p", []) or [])))
 
 

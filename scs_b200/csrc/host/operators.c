@@ -21,14 +21,16 @@ ScsB200ConeWork *scs_b200_init_cone(const ScsCone *k, scs_int m, const scs_float
   int j;
   long long dims;
   if (!k || m <= 0) return SCS_NULL;
-  if (k->cssize > 0) {
-    fprintf(stderr, "scs_b200: the complex-PSD cone is not supported\n");
+  if (k->cssize > 0 && !getenv("SCS_B200_COMPLEX_PSD")) {
+    fprintf(stderr, "scs_b200: the complex-PSD cone is staged, not enabled (set SCS_B200_COMPLEX_PSD=1)\n");
     return SCS_NULL;
   }
+  if (k->cssize < 0 || (k->cssize > 0 && !k->cs)) return SCS_NULL;
   if (k->ep < 0 || k->ed < 0 || k->psize < 0 || (k->psize > 0 && !k->p)) return SCS_NULL;
   dims = (long long)k->z + k->l + k->bsize;
   for (j = 0; j < k->qsize; ++j) dims += k->q[j];
   for (j = 0; j < k->ssize; ++j) dims += ((long long)k->s[j] * (k->s[j] + 1)) / 2;
+  for (j = 0; j < k->cssize; ++j) dims += (long long)k->cs[j] * k->cs[j];
   dims += 3LL * ((long long)k->ep + k->ed + k->psize);
   if (dims != m) {
     fprintf(stderr, "scs_b200: cone dims %lld != m %d\n", dims, m);
@@ -60,6 +62,7 @@ ScsB200ConeWork *scs_b200_init_cone(const ScsCone *k, scs_int m, const scs_float
   bl = bu = SCS_NULL;
   if (!c->cones) goto fail;
   if (b200_cones_set_triples(c->cones, k->ep, k->ed, k->psize, k->p) != 0) goto fail;
+  if (b200_cones_set_complex_psd(c->cones, k->cssize, k->cs, k->ep + k->ed + k->psize) != 0) goto fail;
   c->d_x = (double *)b200_malloc((size_t)m * 8);
   c->d_ry = (double *)b200_malloc((size_t)m * 8);
   if (!c->d_x || !c->d_ry) goto fail;

@@ -134,11 +134,17 @@ static int validate_cones(const ScsData *d, const ScsCone *k) {
     printf("cone dimension error\n");
     return -1;
   }
-  if (k->cssize > 0) {
-    /* scope: zero / LP / box / SOC / PSD + exp / power (8f-3). No CPU fallback. */
-    printf("ERROR: scs_b200 does not support the complex-PSD cone (zero, linear, box, second-order, PSD, "
-           "exponential and power cones are)\n");
+  if (k->cssize > 0 && !getenv("SCS_B200_COMPLEX_PSD")) {
+    /* scope: zero / LP / box / SOC / PSD + exp / power (8f-3). No CPU fallback. The complex
+     * PSD kernels (kernels/cones_complex.cu) are staged and not yet run on hardware: opt in explicitly. */
+    printf("ERROR: scs_b200 does not enable the complex-PSD cone by default (zero, linear, box, second-order, PSD, "
+           "exponential and power cones are supported; SCS_B200_COMPLEX_PSD=1 enables the staged kernels)\n");
     return -1;
+  }
+  if (k->cssize > 0) {
+    if (!k->cs) { printf("complex sd cone array missing\n"); return -1; }
+    for (i = 0; i < k->cssize; ++i)
+      if (k->cs[i] < 0) { printf("complex sd cone dimension error\n"); return -1; }
   }
   if (k->psize > 0) { /* reference cones.c:678-690 */
     if (!k->p) { printf("power cone array missing\n"); return -1; }
@@ -148,6 +154,7 @@ static int validate_cones(const ScsData *d, const ScsCone *k) {
   dims = (long long)k->z + k->l + k->bsize;
   for (i = 0; i < k->qsize; ++i) dims += k->q[i];
   for (i = 0; i < k->ssize; ++i) dims += sd_size(k->s[i]);
+  for (i = 0; i < k->cssize; ++i) dims += (long long)k->cs[i] * k->cs[i];
   dims += 3LL * ((long long)k->ep + k->ed + k->psize);
   if (dims != d->m) {
     printf("Error: Cone dims %li != rows in A %li\n", (long)dims, (long)d->m);
@@ -238,7 +245,7 @@ void scs_finish(ScsWork *w) {
   if (w->d) {
     free_matrix(w->d->A); free_matrix(w->d->P); free(w->d->b); free(w->d->c); free(w->d);
   }
-  if (w->k) { free(w->k->bu); free(w->k->bl); free(w->k->q); free(w->k->s); free(w->k->p); free(w->k); }
+  if (w->k) { free(w->k->bu); free(w->k->bl); free(w->k->q); free(w->k->s); free(w->k->p); free(w->k->cs); free(w->k); }
   free(w->stgs);
   free(w);
 }
@@ -254,12 +261,13 @@ static void set_diag_r_host(ScsWork *w) {
 static int set_cone_boundaries(ScsWork *w) {
   const ScsCone *k = w->k;
   int i, count = 0;
-  int total = k->qsize + k->ssize + k->ep + k->ed + k->psize;
+  int total = k->qsize + k->ssize + k->cssize + k->ep + k->ed + k->psize;
   int *b = (int *)calloc((size_t)total + 1, sizeof(int));
   if (!b) return -1;
   b[count++] = k->z + k->l + k->bsize;
   for (i = 0; i < k->qsize; ++i) b[count++] = k->q[i];
   for (i = 0; i < k->ssize; ++i) b[count++] = sd_size(k->s[i]);
+  for (i = 0; i < k->cssize; ++i) b[count++] = k->cs[i] * k->cs[i];
   for (i = 0; i < k->ep + k->ed + k->psize; ++i) b[count++] = 3; /* every triple shares one D (cones.c:405-408) */
   w->cone_boundaries = b;
   w->cone_boundaries_len = total + 1;
@@ -378,6 +386,7 @@ ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {
   }
   if (k->qsize > 0) { w->k->q = (int *)dup_mem(k->q, (size_t)k->qsize * 4); if (!w->k->q) goto fail; }
   if (k->psize > 0) { w->k->p = (double *)dup_mem(k->p, (size_t)k->psize * 8); if (!w->k->p) goto fail; }
+  if (k->cssize > 0) { w->k->cs = (int *)dup_mem(k->cs, (size_t)k->cssize * 4); if (!w->k->cs) goto fail; }
   if (k->ssize > 0) { w->k->s = (int *)dup_mem(k->s, (size_t)k->ssize * 4); if (!w->k->s) goto fail; }
   *w->stgs = *stgs;
   w->stgs->write_data_filename = SCS_NULL;
@@ -481,7 +490,8 @@ ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {
 
   w->cones = b200_cones_create(m, w->k->z, w->k->l, w->k->bsize, w->k->bl, w->k->bu, w->k->qsize,
                                w->k->q, w->k->ssize, w->k->s);
-  if (!w->cones || b200_cones_set_triples(w->cones, w->k->ep, w->k->ed, w->k->psize, w->k->p) != 0) {
+  if (!w->cones || b200_cones_set_triples(w->cones, w->k->ep, w->k->ed, w->k->psize, w->k->p) != 0 ||
+      b200_cones_set_complex_psd(w->cones, w->k->cssize, w->k->cs, w->k->ep + w->k->ed + w->k->psize) != 0) {
     printf("ERROR: init_cone failure\n");
     goto fail;
   }

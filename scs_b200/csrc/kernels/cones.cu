@@ -77,6 +77,7 @@ struct B200Cones {
   int n_ep, n_ed, n_pow;
   long long tri_off;  // first row of the exponential triples
   double *d_pow;      // power cone parameters (sign = primal / dual), psize
+  B200CpsdCones *cpsd;  // complex PSD blocks (kernels/cones_complex.cu; staged, see there), or NULL
 };
 
 // ------------------------------------------------------------------ SOC kernels
@@ -515,6 +516,7 @@ extern "C" void b200_cones_destroy(B200Cones *c) {
   b200_free(c->d_big); b200_free(c->d_chunk_part); b200_free(c->d_head_a0); b200_free(c->d_psd1_off);
   b200_free(c->d_scratch);
   b200_free(c->d_pow);
+  b200_cpsd_destroy(c->cpsd);
   if (c->groups) {
     for (auto &g : *c->groups) {
       b200_free(g.d_off); b200_free(g.d_mats); b200_free(g.d_evals); b200_free(g.d_info);
@@ -540,6 +542,17 @@ extern "C" int b200_cones_set_triples(B200Cones *c, int ep, int ed, int psize, c
     if (!c->d_pow || b200_h2d(c->d_pow, h_p, (size_t)psize * 8) != 0 || b200_sync() != 0) return -1;
   }
   return 0;
+}
+
+// complex PSD blocks sit between the real PSD blocks and the exponential triples (scs.h cone order)
+extern "C" int b200_cones_set_complex_psd(B200Cones *c, int cssize, const int *h_cs, int n_triples) {
+  long long rows = 0;
+  for (int i = 0; i < cssize; ++i) rows += (long long)h_cs[i] * h_cs[i];
+  if (rows == 0) return 0;
+  const long long first = (long long)c->m - 3LL * n_triples - rows;
+  if (first < 0) return -1;
+  c->cpsd = b200_cpsd_create(cssize, h_cs, first);
+  return c->cpsd ? 0 : -1;
 }
 
 extern "C" int b200_cones_project_rest(B200Cones *c, double *d_x, const double *d_s,
@@ -600,6 +613,8 @@ extern "C" int b200_cones_project_rest(B200Cones *c, double *d_x, const double *
       b200_count_launch(1);
     }
   }
+  // ---- complex PSD
+  if (c->cpsd && b200_cpsd_project(c->cpsd, d_x, d_s, d_ry) != 0) return -1;
   // ---- exponential / power triples
   if (c->n_ep + c->n_ed + c->n_pow > 0) {
     if (b200_cone_triples_project(c->n_ep, c->n_ed, c->n_pow, c->tri_off, c->d_pow, d_x, d_s, d_ry) != 0)

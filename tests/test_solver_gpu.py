@@ -246,7 +246,7 @@ def test_unsupported_cone_fails_loudly(lib):
     prob = small_problem("lp", seed=1)
     cone = dict(prob["cone"])
     cone["l"] -= 4
-    cone["cs"] = [2]          # complex PSD cone of order 2 = 4 rows: not on the device path
+    cone["cs"] = [2]          # complex PSD cone of order 2 = 4 rows: staged, refused unless SCS_B200_COMPLEX_PSD=1
     hp = capi.HostProblem(prob["A"], prob["b"], prob["c"], cone)
     st = capi.default_settings(lib, verbose=0)
     assert not lib.scs_init(C.byref(hp.data), C.byref(hp.cone), C.byref(st))

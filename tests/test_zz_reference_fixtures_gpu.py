@@ -91,3 +91,32 @@ def test_exp_power_operator_matches_committed_goldens(lib):
             assert err.max() <= 1e-8 and np.median(err) <= 1e-14, (tag, err.max())
     finally:
         lib.scs_b200_finish_cone(cw)
+
+
+def test_complex_psd_operator_matches_reference(lib, reflib, monkeypatch):
+    """staged complex-PSD kernels (kernels/cones_complex.cu, opt-in) against the reference's zheevr projection"""
+    if not lib.scs_b200_device_ok():
+        pytest.skip("no sm_100 device")
+    monkeypatch.setenv("SCS_B200_COMPLEX_PSD", "1")
+    reflib._scs_init_cone.restype = C.c_void_p
+    reflib._scs_init_cone.argtypes = [PP(capi.ScsCone), C.c_int]
+    reflib._scs_proj_dual_cone.argtypes = [capi.c_double_p, C.c_void_p, C.c_void_p, capi.c_double_p]
+    reflib._scs_finish_cone.argtypes = [C.c_void_p]
+    rng = np.random.default_rng(5)
+    for cone in ({"cs": [1, 2, 3, 5, 12, 12, 40]}, {"z": 2, "l": 3, "q": [4], "s": [3], "cs": [4, 7], "ep": 2, "p": [0.4]}):
+        m = capi.cone_rows(cone)
+        x = rng.standard_normal(m) * 2
+        for ry in (None, np.full(m, 10.0)):
+            k, keep = capi.make_cone(cone)
+            cw = reflib._scs_init_cone(C.byref(k), m)
+            ref = x.copy()
+            assert reflib._scs_proj_dual_cone(capi.dptr(ref), cw, None, capi.dptr(None if ry is None else ry.copy())) == 0
+            reflib._scs_finish_cone(cw)
+            k2, keep2 = capi.make_cone(cone)
+            mw = lib.scs_b200_init_cone(C.byref(k2), m, None)
+            assert mw
+            out = x.copy()
+            assert lib.scs_b200_proj_dual_cone(mw, capi.dptr(out), capi.dptr(None if ry is None else ry.copy())) == 0
+            lib.scs_b200_finish_cone(mw)
+            err = np.abs(out - ref).max() / max(np.abs(ref).max(), 1.0)
+            assert err <= (1e-8 if cone.get("p") else 5e-13), (cone, err)

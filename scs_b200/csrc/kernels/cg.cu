@@ -21,7 +21,9 @@
 #include "../common.cuh"
 #include "../dev_api.h"
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
+#include <vector>
 
 #define VEC_THREADS B200_RED_THREADS
 
@@ -466,6 +468,213 @@ k_cg_finish_p2p2(int n, double *__restrict__ y, P2pView pv, unsigned long long s
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// STAGED (written after round 1's GPU budget was spent; NOT yet run on hardware; off unless
+// SCS_B200_SHARD_X=1 / scs_b200_set_shard_x(1)): "sharded-x" CG iteration for G >= 2 ranks.
+// p stays replicated (it is the SpMV gather vector); x, r, z and Gp are owned by n-slices
+// [n g/G, n (g+1)/G). After K1 / K2 (the rank's partial A_g' R_g^-1 A_g p sits in its exchange buffer and
+// "partial ready" is signalled) ONE cooperative kernel per rank does the rest of the iteration:
+//   1  wait for all partials; reduce MY slice in rank order (remote loads), Gp = R_x p (+ P p) + sum,
+//      block-reduce p'Gp over the slice; the last block publishes the slice's p'Gp to every rank;
+//   2  wait for the G partial scalars, add them in rank order => p'Gp and alpha, identical bits everywhere;
+//   3  K3 on the slice (x, r, z; z'r and ||r||_inf partials), published the same way;
+//   4  wait, combine => z'r, ||r||_inf, the stop decision and beta, identical everywhere;
+//   5  K4 on the slice: p = z + beta p, written to the local p and to the rank's p-exchange buffer; the last
+//      block records the iteration in the control block and publishes "p slice ready";
+//   6  wait, copy the other ranks' p slices into the local p.
+// Remote volume 2 (G-1)/G n doubles as in the two-phase reduction, but K3 / K4 shrink by G and no rank
+// touches a full n-vector except p. All blocks spin on flags, so the grid must be co-resident (<= #SMs).
+// Exchange memory: the rank's partial buffer red[2][n], its p-exchange buffer (the rs[2][n] area of the
+// two-phase mode), flag slots 0..7 "partial", 16..23 / 24..31 "scalars of round 1 / 2", 32..39 "p slice",
+// and 64 doubles of scalar slots after the flag line: [round][parity][rank][2].
+struct P2pViewX {
+  int nranks, rank, stride;
+  const double *base[8];
+  unsigned long long *flags[8];
+};
+__device__ __forceinline__ double *px_scal(const P2pViewX &pv, int r, int round, int parity, int from) {
+  return reinterpret_cast<double *>(pv.flags[r] + 64) + (((round * 2 + parity) * 8 + from) * 2);
+}
+__device__ __forceinline__ void px_wait(volatile unsigned long long *line, int first, int G, int skip_rank,
+                                        unsigned long long seq, B200CgCtl *ctl) {
+  const long long t0 = clock64();
+  for (int r = 0; r < G; ++r) {
+    if (r == skip_rank) continue;
+    while (line[first + r] < seq) {
+      if (clock64() - t0 > 20000000000LL) { ctl->pad[0] = 1; break; }  // ~10 s: never hang the GPU
+    }
+  }
+  __threadfence_system();
+}
+
+__global__ void __launch_bounds__(VEC_THREADS)
+k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int do_signal, int y_has_px,
+                const double *__restrict__ rx, const double *__restrict__ M, double *__restrict__ p,
+                double *__restrict__ Gp, double *__restrict__ x, double *__restrict__ r,
+                double *__restrict__ z, B200CgCtl *ctl, double *partials, unsigned int *counters) {
+  if (ctl->done) return;
+  __shared__ double s_red[128];
+  __shared__ double s_bc[4];
+  const int G = pv.nranks, me = pv.rank;
+  const int parity = (int)(seq & 1ull);
+  const size_t slot = (size_t)parity * pv.stride;
+  const size_t pex = (size_t)2 * pv.stride + slot;
+  const long long lo = (long long)n * me / G, hi = (long long)n * (me + 1) / G;
+  const long long gstride = (long long)gridDim.x * blockDim.x;
+  const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  volatile unsigned long long *myflags = pv.flags[me];
+  // values of the control block as of the start of the iteration (the last block rewrites it at the end)
+  const double ztr_old = ctl->ztr, tol = ctl->tol;
+  const int iters_old = ctl->iters, max_its = ctl->max_its;
+
+  // ---- 1: partials ready -> my slice of G p, partial p'Gp
+  if (threadIdx.x == 0) {
+    if (do_signal && blockIdx.x == 0) {
+      __threadfence_system();
+      for (int q = 0; q < G; ++q)
+        if (q != me) *((volatile unsigned long long *)(pv.flags[q] + me)) = seq;
+    }
+    px_wait(myflags, 0, G, me, seq, ctl);
+  }
+  __syncthreads();
+  double acc = 0.0;
+  for (long long i = lo + gtid; i < hi; i += gstride) {
+    double sum = 0.0;
+    for (int q = 0; q < G; ++q) sum += __ldcg(pv.base[q] + slot + i);  // rank order
+    const double base = y_has_px ? Gp[i] + sum : sum;
+    const double pi = p[i];
+    const double out = fma(rx[i], pi, base);
+    Gp[i] = out;
+    acc = fma(pi, out, acc);
+  }
+  {
+    double a[1] = {acc};
+    block_sum<1>(a, s_red);
+    if (threadIdx.x == 0) {
+      partials[blockIdx.x] = a[0];
+      __threadfence();
+      if (atomicAdd(&counters[4], 1u) == gridDim.x - 1) {
+        counters[4] = 0u;
+        __threadfence();
+        double tot = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) tot += __ldcg(&partials[b]);  // block order
+        for (int q = 0; q < G; ++q) px_scal(pv, q, 0, parity, me)[0] = tot;
+        __threadfence_system();
+        for (int q = 0; q < G; ++q) *((volatile unsigned long long *)(pv.flags[q] + 16 + me)) = seq;
+      }
+      // ---- 2: all partial scalars -> alpha
+      px_wait(myflags, 16, G, -1, seq, ctl);
+      double pGp = 0.0;
+      for (int q = 0; q < G; ++q) pGp += *((volatile double *)px_scal(pv, me, 0, parity, q));
+      s_bc[0] = pGp;
+      s_bc[1] = ztr_old / pGp;
+    }
+  }
+  __syncthreads();
+  const double pGp = s_bc[0], alpha = s_bc[1], nalpha = -alpha;
+
+  // ---- 3: K3 on the slice
+  double acc0 = 0.0, acc1 = 0.0;
+  for (long long i = lo + gtid; i < hi; i += gstride) {
+    const double pi = p[i];
+    const double xi = fma(alpha, pi, x[i]);
+    const double ri = fma(nalpha, Gp[i], r[i]);
+    const double zi = ri * M[i];
+    x[i] = xi;
+    r[i] = ri;
+    z[i] = zi;
+    acc0 = fma(zi, ri, acc0);
+    acc1 = fmax(acc1, fabs(ri));
+  }
+  {
+    double sm[1] = {acc0}, mx[1] = {acc1};
+    block_sum<1>(sm, s_red);
+    block_max<1>(mx, s_red + 64);
+    if (threadIdx.x == 0) {
+      partials[2048 + blockIdx.x] = sm[0];
+      partials[4096 + blockIdx.x] = mx[0];
+      __threadfence();
+      if (atomicAdd(&counters[5], 1u) == gridDim.x - 1) {
+        counters[5] = 0u;
+        __threadfence();
+        double t0 = 0.0, t1 = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) {
+          t0 += __ldcg(&partials[2048 + b]);
+          t1 = fmax(t1, __ldcg(&partials[4096 + b]));
+        }
+        for (int q = 0; q < G; ++q) {
+          double *sl = px_scal(pv, q, 1, parity, me);
+          sl[0] = t0;
+          sl[1] = t1;
+        }
+        __threadfence_system();
+        for (int q = 0; q < G; ++q) *((volatile unsigned long long *)(pv.flags[q] + 24 + me)) = seq;
+      }
+      // ---- 4: z'r, ||r||_inf, stop decision, beta (same arithmetic as k_cg_update's last block)
+      px_wait(myflags, 24, G, -1, seq, ctl);
+      double ztr = 0.0, rn = 0.0;
+      for (int q = 0; q < G; ++q) {
+        volatile double *sl = px_scal(pv, me, 1, parity, q);
+        ztr += sl[0];
+        rn = fmax(rn, sl[1]);
+      }
+      int done = 0;
+      double beta = 0.0;
+      if (rn < tol) done = 1;
+      else if (ztr_old == 0.0) done = 1;
+      else {
+        beta = ztr / ztr_old;
+        if (iters_old + 1 >= max_its) done = 1;
+      }
+      s_bc[0] = ztr;
+      s_bc[1] = rn;
+      s_bc[2] = beta;
+      s_bc[3] = (double)done;
+    }
+  }
+  __syncthreads();
+  const double ztr_new = s_bc[0], rnorm = s_bc[1], beta = s_bc[2];
+  const int done = s_bc[3] != 0.0;
+
+  // ---- 5: K4 on the slice (skipped once the stop test fired, like k_cg_pupdate)
+  if (!done) {
+    double *mine = const_cast<double *>(pv.base[me]) + pex;
+    for (long long i = lo + gtid; i < hi; i += gstride) {
+      const double pn = fma(beta, p[i], z[i]);
+      p[i] = pn;
+      mine[i] = pn;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(&counters[6], 1u) == gridDim.x - 1) {
+      counters[6] = 0u;
+      ctl->ztr_prev = ztr_old;
+      ctl->ztr = ztr_new;
+      ctl->rnorm = rnorm;
+      ctl->pGp = pGp;
+      ctl->alpha = alpha;
+      ctl->iters = iters_old + 1;
+      if (!done) ctl->beta = beta;
+      if (done) ctl->done = 1;
+      __threadfence_system();
+      for (int q = 0; q < G; ++q) *((volatile unsigned long long *)(pv.flags[q] + 32 + me)) = seq;
+    }
+    // ---- 6: the other slices of the new p
+    if (!done) px_wait(myflags, 32, G, -1, seq, ctl);
+  }
+  __syncthreads();
+  if (done) return;
+  for (int q = 0; q < G; ++q) {
+    if (q == me) continue;
+    const long long qlo = (long long)n * q / G, qhi = (long long)n * (q + 1) / G;
+    const double *src = pv.base[q] + pex;
+    for (long long i = qlo + gtid; i < qhi; i += gstride) p[i] = __ldcg(src + i);
+  }
+}
+
 __global__ void k_add_if_not(int n, double *__restrict__ a, const double *__restrict__ b, const int *skip) {
   if (skip != nullptr && *skip) return;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a[i] += b[i];
@@ -605,7 +814,57 @@ static int mat_vec(B200Cg *cg, const double *d_x, double *d_y, int with_dot, con
   return b200_spmv(cg->At, &a);
 }
 
+// staged sharded-x mode (see k_cgx_iteration): -1 = read SCS_B200_SHARD_X once, 0 = off (default), 1 = on
+static int g_shard_x = -1;
+extern "C" void scs_b200_set_shard_x(int on) { g_shard_x = on ? 1 : 0; }
+static int shard_x_active(const B200Cg *cg) {
+  if (g_shard_x < 0) {
+    const char *e = getenv("SCS_B200_SHARD_X");
+    g_shard_x = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return g_shard_x == 1 && cg->nranks > 1 && cg->use_p2p && cg->d_p2p_sig != nullptr;
+}
+
+static int cg_iteration_shard_x(B200Cg *cg, double *d_x) {
+  cudaStream_t st = (cudaStream_t)b200_stream();
+  const int *d_skip = &cg->d_ctl->done;
+  B200SpmvArgs a;
+  memset(&a, 0, sizeof(a));
+  // K1 (local rows): tmp_g = (A_g p) ./ R_g
+  a.d_x = cg->d_p; a.d_y = cg->d_tmp + cg->row0; a.init_sign = 1.0; a.post = B200_POST_DIV;
+  a.d_d = cg->d_ry + cg->row0; a.d_skip = d_skip;
+  if (b200_spmv(cg->A, &a) != 0) return -1;
+  // K2: partial A_g' tmp_g into this rank's exchange buffer; its last block signals "partial ready"
+  const unsigned long long seq = b200_p2p_next_seq();
+  a.d_x = cg->d_tmp + cg->row0;
+  a.d_y = b200_p2p_base(b200_comm_rank()) + (size_t)(seq & 1ull) * b200_p2p_stride();
+  a.post = B200_POST_NONE; a.d_d = nullptr;
+  a.hook = B200_HOOK_P2P_SIGNAL; a.d_hook_arg = cg->d_p2p_sig; a.hook_val = seq;
+  if (b200_spmv(cg->At, &a) != 0) return -1;
+  if (cg->P) {  // P is replicated: Gp = P p on every rank, the slice kernel adds the rest
+    memset(&a, 0, sizeof(a));
+    a.d_x = cg->d_p; a.d_y = cg->d_Gp; a.init_sign = 1.0; a.post = B200_POST_NONE; a.d_skip = d_skip;
+    if (b200_spmv(cg->P, &a) != 0) return -1;
+  }
+  P2pViewX pv;
+  pv.nranks = cg->nranks; pv.rank = b200_comm_rank(); pv.stride = b200_p2p_stride();
+  for (int r = 0; r < 8; ++r) {
+    pv.base[r] = r < cg->nranks ? b200_p2p_base(r) : nullptr;
+    pv.flags[r] = r < cg->nranks ? b200_p2p_flags(r) : nullptr;
+  }
+  int g = b200_num_sms();  // every block spins on flags: one block per SM, co-resident
+  const long long slice = ((long long)cg->n + cg->nranks - 1) / cg->nranks;
+  const long long want = (slice + VEC_THREADS - 1) / VEC_THREADS;
+  if (want < g) g = (int)(want < 1 ? 1 : want);
+  k_cgx_iteration<<<g, VEC_THREADS, 0, st>>>(cg->n, pv, seq, 0, cg->P != nullptr, cg->d_rx, cg->d_M, cg->d_p,
+                                             cg->d_Gp, d_x, cg->d_r, cg->d_z, cg->d_ctl, cg->d_partials,
+                                             cg->d_counter);
+  b200_count_launch(1);
+  return 0;
+}
+
 static int cg_iteration(B200Cg *cg, double *d_x) {
+  if (shard_x_active(cg)) return cg_iteration_shard_x(cg, d_x);
   cudaStream_t st = (cudaStream_t)b200_stream();
   const int n = cg->n;
   int g = (n + VEC_THREADS * 8 - 1) / (VEC_THREADS * 8);
@@ -686,6 +945,12 @@ extern "C" int b200_cg_solve(B200Cg *cg, double *d_b, const double *d_s, double 
     if (enq >= (long long)max_its + 1) break;  // safety; device sets done at max_its
     // cold solves (no hint) grow geometrically up to 256 per poll
     batch = its_hint > 0 ? follow : (batch < 256 ? batch * 2 : 256);
+  }
+  if (shard_x_active(cg) && !cg->h_ctl->skip) {
+    // sharded-x mode: every rank owns a slice of x; all ranks need all of it for the back-substitution
+    std::vector<int> xoff((size_t)cg->nranks + 1);
+    for (int q = 0; q <= cg->nranks; ++q) xoff[(size_t)q] = (int)((long long)n * q / cg->nranks);
+    if (b200_allgatherv(d_b, xoff.data()) != 0) return -1;
   }
   // y = R_y^{-1} (A x - r_y)   (private.c:313-317)
   if (cg->nranks > 1) {

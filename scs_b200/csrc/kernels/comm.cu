@@ -148,7 +148,7 @@ extern "C" int b200_p2p_setup(int n) {
   if (!N_AllGather) *(void **)(&N_AllGather) = dlsym(N.h, "ncclAllGather");
   if (!N_AllGather) return -1;
   cudaStream_t st = (cudaStream_t)b200_stream();
-  const size_t bytes = ((size_t)4 * n + 64) * 8;
+  const size_t bytes = ((size_t)4 * n + 64 + 64) * 8;  // + 64 flags + 64 scalar slots (staged sharded-x mode)
   double *mine = (double *)b200_malloc(bytes);
   if (!mine) return -1;
   if (b200_memset0(mine, bytes) != 0) return -1;

@@ -84,6 +84,27 @@ if os.environ.get("MGPU_TIME", "1") != "0":
         if rank == 0:
             print(f"[C2 sharded over {world} GPUs] CG iteration, {label}: {float(t[0])*1e3:.1f} us", flush=True)
     lib.scs_b200_set_p2p_mode(0)
+    if os.environ.get("MGPU_SHARD_X"):
+        # STAGED mode (kernels/cg.cu k_cgx_iteration, not yet run on hardware): time it, then check a solve
+        lib.scs_b200_set_shard_x.argtypes = [C.c_int]
+        lib.scs_b200_set_shard_x(1)
+        ms = lib.scs_b200_time_cg_iter(w, 30, C.byref(ab))
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            print(f"[C2 sharded over {world} GPUs] CG iteration, sharded-x (staged): {float(t[0])*1e3:.1f} us", flush=True)
+        rng2 = np.random.default_rng(99)
+        rhs = rng2.standard_normal(n + m)
+        mine = rhs.copy()
+        assert lib.scs_solve_lin_sys(w, capi.dptr(mine), None, 1e-10) == 0
+        lib.scs_b200_set_shard_x(0)
+        base = rhs.copy()
+        assert lib.scs_solve_lin_sys(w, capi.dptr(base), None, 1e-10) == 0
+        rel = np.abs(mine - base).max() / np.abs(base).max()
+        if rank == 0:
+            print(f"[C2 sharded over {world} GPUs] KKT solve, sharded-x vs default sharded mode: rel diff {rel:.2e} "
+                  f"-> {'OK' if rel <= 1e-8 else 'FAIL'}", flush=True)
+        ok = ok and rel <= 1e-8
     lib.scs_free_lin_sys_work(w)
 lib.scs_b200_comm_finalize()
 flag = torch.tensor([1 if ok else 0], device="cuda")

@@ -229,6 +229,70 @@ k_cg_pupdate(int n, double *__restrict__ p, const double *__restrict__ z, const 
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = fma(beta, p[n - 1], z[n - 1]);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// STAGED (not yet run on hardware; off unless SCS_B200_FUSE_K34=1): K3 and K4 in one cooperative launch.
+// K4 needs beta = z'r / z'r_prev, i.e. the grid-wide reduction of K3: the last block to finish K3 combines the
+// block partials in index order (same arithmetic as k_cg_update), updates the control block and releases a
+// generation flag; every block waits for it (one block per SM at most two, all co-resident) and then runs K4
+// on the elements it still has in L1 / L2. Saves one launch gap and the second pass's ramp-up per CG iteration.
+__global__ void __launch_bounds__(VEC_THREADS)
+k_cg_update_fused(int n, double *__restrict__ x, double *__restrict__ r, double *__restrict__ p,
+                  const double *__restrict__ Gp, const double *__restrict__ M, double *__restrict__ z,
+                  B200CgCtl *ctl, double *partials, unsigned int *counters, unsigned int gen) {
+  if (ctl->done) return;
+  __shared__ double s_red[128];
+  const double alpha = ctl->alpha, nalpha = -alpha;
+  const double ztr_old = ctl->ztr;
+  double acc0 = 0.0, acc1 = 0.0;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double xv = x[i], rv = r[i], zv;
+    cg_update_elem(alpha, nalpha, xv, rv, p[i], Gp[i], M[i], zv, acc0, acc1);
+    x[i] = xv; r[i] = rv; z[i] = zv;
+  }
+  double sm[1] = {acc0}, mx[1] = {acc1};
+  block_sum<1>(sm, s_red);
+  block_max<1>(mx, s_red + 64);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = sm[0];
+    partials[2048 + blockIdx.x] = mx[0];
+    __threadfence();
+    if (atomicAdd(&counters[8], 1u) == gridDim.x - 1) {
+      counters[8] = 0u;
+      __threadfence();
+      double t0 = 0.0, t1 = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b) {
+        t0 += __ldcg(&partials[b]);
+        t1 = fmax(t1, __ldcg(&partials[2048 + b]));
+      }
+      ctl->ztr_prev = ztr_old;
+      ctl->ztr = t0;
+      ctl->rnorm = t1;
+      ctl->iters += 1;
+      if (t1 < ctl->tol) {
+        ctl->done = 1;
+      } else if (ztr_old == 0.0) {
+        ctl->done = 1;
+      } else {
+        ctl->beta = t0 / ztr_old;
+        if (ctl->iters >= ctl->max_its) ctl->done = 1;
+      }
+      __threadfence();
+      *((volatile unsigned int *)&counters[9]) = gen;  // release
+    }
+    const long long t0c = clock64();
+    while (*((volatile unsigned int *)&counters[9]) != gen) {
+      if (clock64() - t0c > 20000000000LL) { ctl->pad[0] = 1; break; }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  if (*((volatile int *)&ctl->done)) return;
+  const double beta = *((volatile double *)&ctl->beta);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = fma(beta, p[i], z[i]);
+}
+
 __global__ void k_zero_if(long long len, double *__restrict__ v, const int *flag) {
   if (!*flag) return;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < len;
@@ -871,6 +935,22 @@ static int cg_iteration(B200Cg *cg, double *d_x) {
   if (g > 2 * b200_num_sms()) g = 2 * b200_num_sms();
   if (g < 1) g = 1;
   if (mat_vec(cg, cg->d_p, cg->d_Gp, 1, &cg->d_ctl->done) != 0) return -1;
+  {
+    static int fuse = -1;
+    static unsigned int gen = 0;
+    if (fuse < 0) {
+      const char *e = getenv("SCS_B200_FUSE_K34");
+      fuse = (e && atoi(e) != 0) ? 1 : 0;
+    }
+    if (fuse) {  // staged: K3 + K4 in one cooperative launch (all blocks co-resident: <= 2 per SM)
+      ++gen;
+      if (gen == 0) ++gen;
+      k_cg_update_fused<<<g, VEC_THREADS, 0, st>>>(n, d_x, cg->d_r, cg->d_p, cg->d_Gp, cg->d_M, cg->d_z, cg->d_ctl,
+                                                   cg->d_partials, cg->d_counter, gen);
+      b200_count_launch(1);
+      return 0;
+    }
+  }
   k_cg_update<<<g, VEC_THREADS, 0, st>>>(n, d_x, cg->d_r, cg->d_p, cg->d_Gp, cg->d_M, cg->d_z,
                                          cg->d_ctl, cg->d_partials, cg->d_counter);
   k_cg_pupdate<<<g, VEC_THREADS, 0, st>>>(n, cg->d_p, cg->d_z, cg->d_ctl);

@@ -120,3 +120,36 @@ def test_complex_psd_operator_matches_reference(lib, reflib, monkeypatch):
             lib.scs_b200_finish_cone(mw)
             err = np.abs(out - ref).max() / max(np.abs(ref).max(), 1.0)
             assert err <= (1e-8 if cone.get("p") else 5e-13), (cone, err)
+
+
+@pytest.mark.parametrize("cfg,steps", [("C3", 25), ("C4", 40), ("C5", 25)])
+def test_full_size_configs_are_self_consistent(lib, cfg, steps):
+    """BASELINE configs 2-4 at FULL size (C3: LP n=5e6, nnz=5e7; C4: 200 PSD(100) blocks; C5: mixed, n=2e6, nnz=3e7):
+    a fixed number of ADMM iterations, then the size-independent checks the reference applies to every solve
+    (test/problem_utils.h:209-243): the reported residuals equal the ones recomputed on the host from (x, y, s) in
+    fp64, s is in the cone and y in the dual cone, the duality gap is what the objectives say."""
+    if not lib.scs_b200_device_ok():
+        pytest.skip("no sm_100 device")
+    from scs_b200 import problems
+    prob = problems.config(cfg)
+    hp = capi.HostProblem(prob["A"], prob["b"], prob["c"], prob["cone"])
+    st = capi.default_settings(lib, verbose=0, max_iters=steps, eps_abs=1e-12, eps_rel=1e-12)
+    x, y, s = np.zeros(hp.n), np.zeros(hp.m), np.zeros(hp.m)
+    sol = capi.ScsSolution(capi.dptr(x), capi.dptr(y), capi.dptr(s))
+    info = capi.ScsInfo()
+    status = lib.scs(C.byref(hp.data), C.byref(hp.cone), C.byref(st), C.byref(sol), C.byref(info))
+    assert status == 2 and info.iter == steps, (status, info.status)          # solved (inaccurate - reached max_iters)
+    A = prob["A"]
+    res_pri = np.abs(problems.csc_matvec(A, x) + s - prob["b"]).max()
+    res_dual = np.abs(problems.csc_rmatvec(A, y) + prob["c"]).max()
+    scale = max(1.0, np.abs(prob["b"]).max(), np.abs(prob["c"]).max())
+    assert abs(res_pri - info.res_pri) <= 1e-9 * scale, (res_pri, info.res_pri)
+    assert abs(res_dual - info.res_dual) <= 1e-9 * scale, (res_dual, info.res_dual)
+    pobj, dobj = float(prob["c"] @ x), -float(prob["b"] @ y)
+    assert abs(pobj - info.pobj) <= 1e-9 * max(1.0, abs(pobj)) and abs(dobj - info.dobj) <= 1e-9 * max(1.0, abs(dobj))
+    assert abs(abs(pobj - dobj) - info.gap) <= 1e-9 * max(1.0, abs(pobj), abs(dobj))
+    # cone membership of the returned s and y (projection is idempotent on them)
+    smax = max(1.0, np.abs(s).max())
+    assert np.abs(problems.proj_cone(s, prob["cone"]) - s).max() <= 1e-9 * smax
+    ymax = max(1.0, np.abs(y).max())
+    assert np.abs(problems.proj_dual_cone(y, prob["cone"]) - y).max() <= 1e-9 * ymax

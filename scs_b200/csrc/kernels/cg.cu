@@ -1011,6 +1011,7 @@ extern "C" int b200_cg_solve(B200Cg *cg, double *d_b, const double *d_s, double 
   if (batch > 4096) batch = 4096;
   const int follow = its_hint / 8 > 8 ? (its_hint / 8 < 256 ? its_hint / 8 : 256) : 8;
   long long enq = 0;
+  int polls = 0;
   for (;;) {
     for (int i = 0; i < batch; ++i)
       if (cg_iteration(cg, d_b) != 0) return -1;
@@ -1023,8 +1024,11 @@ extern "C" int b200_cg_solve(B200Cg *cg, double *d_b, const double *d_s, double 
     }
     if (cg->h_ctl->done) break;
     if (enq >= (long long)max_its + 1) break;  // safety; device sets done at max_its
-    // cold solves (no hint) grow geometrically up to 256 per poll
-    batch = its_hint > 0 ? follow : (batch < 256 ? batch * 2 : 256);
+    // after a miss: a small batch first (the hint is usually only slightly short), then geometric growth up
+    // to 256 per poll (cold solves, or a solve that needs many more iterations than the previous one)
+    ++polls;
+    if (its_hint > 0 && polls == 1) batch = follow;
+    else batch = batch < 128 ? batch * 2 : 256;
   }
   if (shard_x_active(cg) && !cg->h_ctl->skip) {
     // sharded-x mode: every rank owns a slice of x; all ranks need all of it for the back-substitution

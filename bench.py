@@ -351,6 +351,17 @@ def main():
     iters = int(info.iter)
     lib.scs_finish(w)
 
+    # ---- optional (SCS_BENCH_TTE=1): time to the default stopping criterion eps_abs = eps_rel = 1e-4, the second
+    # half of BASELINE.json's metric; a separate full solve so that the K-step timing above is untouched
+    tte = None
+    if os.environ.get("SCS_BENCH_TTE"):
+        w2, info_t, _ = run_solver(lib, capi, hp, dict(max_iters=100000))
+        lib.scs_finish(w2)
+        tte = {"status": info_t.status.decode(errors="replace"), "iters": int(info_t.iter),
+               "solve_s": info_t.solve_time / 1e3, "setup_s": info_t.setup_time / 1e3, "pobj": info_t.pobj,
+               "known_optimum": prob.get("opt"), "res_pri": info_t.res_pri, "res_dual": info_t.res_dual,
+               "gap": info_t.gap}
+
     # max over ranks / sum of work
     tmax = solve_s
     if world > 1:
@@ -423,6 +434,11 @@ def main():
             "lin_sys_ms": info.lin_sys_time, "cone_ms": info.cone_time, "accel_ms": info.accel_time,
             "setup_ms": info.setup_time, "problem_gen_s": gen_s,
         })
+        if tte:
+            # the CPU reference needs hours for this: its time is extrapolated from its measured iterations/s
+            if cpu_base and cpu_base.get("value"):
+                tte["cpu_reference_extrapolated_s"] = tte["iters"] / cpu_base["value"]
+            out["time_to_eps_1e-4"] = tte
         if roof:
             out["roofline"] = roof
         if cpu_base:

@@ -8,10 +8,10 @@ L=gpurun_out/round2_first.log
 echo "=== staged tests (-m gpu_unverified)" >> $L
 timeout 600 python -m pytest tests -q -m gpu_unverified -s 2>&1 | tail -25 >> $L
 echo "=== bench (no cpu baseline)" >> $L
-timeout 600 python bench.py --steps 100 --warmup 5 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
+SCS_BENCH_TTE=1 timeout 900 python bench.py --steps 100 --warmup 5 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.readline())
-print({k:d[k] for k in ('value','ms_per_step','cg_iters_per_step','gpu_launches','lin_sys_ms','setup_ms')}, 'e2e', d['e2e']['value'], 'frac', d['roofline']['frac'])" >> $L
+print({k:d[k] for k in ('value','ms_per_step','cg_iters_per_step','gpu_launches','lin_sys_ms','setup_ms')}, 'e2e', d['e2e']['value'], 'frac', d['roofline']['frac'], 'tte', d.get('time_to_eps_1e-4'))" >> $L
 echo "=== staged: K3+K4 fused (SCS_B200_FUSE_K34=1): linsys + solver tests, CG iteration timing" >> $L
 SCS_B200_FUSE_K34=1 timeout 600 python -m pytest tests/test_linsys_gpu.py tests/test_solver_gpu.py -x -q -m gpu 2>&1 | tail -3 >> $L
 REPS=20 timeout 300 python scripts/prof_spmv.py 2>&1 | tail -1 >> $L

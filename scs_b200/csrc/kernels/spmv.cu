@@ -83,6 +83,10 @@ struct B200Spmv {
   long long stored;  // entries held in d_colidx / d_vals (v3: nnz + one explicit zero per empty row)
   int4 *d_wt3;       // v3 warp-tile descriptors, padded per CTA to groups of SPMV3_NCW
   int *d_cta_begin3; // v3: first group of every CTA
+  // STAGED long-row support (SCS_B200_SPMV_LONGROWS=1): virtual rows + combine pass, see Spmv3Plan::vptr
+  int nvrows;        // virtual rows (== nrows when no row was cut)
+  int *d_vptr;       // nrows+1, or NULL
+  double *d_vscratch;  // nvrows partial sums
 };
 
 static size_t spmv_smem_bytes() {
@@ -829,6 +833,55 @@ spmv_flag_kernel(const int *__restrict__ colidx, const double *__restrict__ vals
   }
 }
 
+
+// STAGED (not yet run on hardware): second pass of the long-row mode. The flag kernel has written one sum per
+// VIRTUAL row into `part`; thread r adds the pieces of true row r in order, applies the epilogue and the same
+// deterministic dot / hook tail as the one-pass kernels.
+template <int POST>
+__global__ void __launch_bounds__(256)
+spmv_combine_kernel(int nrows, const int *__restrict__ vptr, const double *__restrict__ part,
+                    double *__restrict__ y, const double *init, double init_sign, const double *__restrict__ d,
+                    const double *__restrict__ v, double *dot_out, int hook, void *hook_arg, const int *skip,
+                    double *partials, unsigned int *counter, unsigned long long hook_val) {
+  if (skip != nullptr && *((volatile const int *)skip) != 0) return;
+  __shared__ double s_red[64];
+  double dot_acc = 0.0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int q = vptr[r]; q < vptr[r + 1]; ++q) s = __dadd_rn(s, part[q]);
+    if (init != nullptr) s = __dadd_rn(s, init_sign * init[r]);
+    spmv_epilogue<POST>(s, r, y, d, v, dot_acc);
+  }
+  if (hook == B200_HOOK_P2P_SIGNAL) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned tk = atomicAdd(counter, 1u);
+      if (tk == gridDim.x - 1) {
+        *counter = 0u;
+        __threadfence_system();
+        const B200P2pSignal *ps = reinterpret_cast<const B200P2pSignal *>(hook_arg);
+        for (int q = 0; q < ps->nranks; ++q)
+          if (q != ps->rank) *((volatile unsigned long long *)(ps->flags[q] + ps->rank)) = hook_val;
+      }
+    }
+  }
+  if (POST == B200_POST_FMA_DOT) {
+    double accd[1] = {dot_acc};
+    block_sum<1>(accd, s_red);
+    if (grid_finish<1>(accd, partials, counter, 0u, s_red)) {
+      if (threadIdx.x == 0) {
+        *dot_out = accd[0];
+        if (hook == B200_HOOK_CG_ALPHA) {
+          B200CgCtl *c = reinterpret_cast<B200CgCtl *>(hook_arg);
+          c->pGp = accd[0];
+          c->alpha = c->ztr / accd[0];
+        }
+      }
+    }
+  }
+}
+
 // ---- host side of v3: the flagged stream, its warp-tiles and the static CTA partition.
 // Pure host code (no CUDA calls): also exported for the CPU tests (tests/test_spmv_plan_cpu.py
 // re-executes the kernel's lane algorithm on this plan in numpy).
@@ -847,18 +900,27 @@ struct Spmv3Plan {
   std::vector<int> cta_begin;  // grid+1, in groups of SPMV3_NCW descriptors
   int grid = 0;
   int nwt = 0;               // real warp-tiles
+  // STAGED long-row support: a row longer than SPMV3_MAXROW is cut into pieces ("virtual rows", an END flag at
+  // the end of every piece); the kernel then produces one sum per virtual row and a combine pass adds the
+  // pieces of each true row. vptr[r] = first virtual row of true row r (empty when no row was cut).
+  std::vector<int> vptr;
+  int nvrows = 0;
 };
 
 static bool spmv3_build_plan(int nrows, int ncols, const int *rp, const int *ci, const double *va,
-                             int grid_cap, Spmv3Plan &P) {
+                             int grid_cap, Spmv3Plan &P, bool split_long = false) {
   if (nrows <= 0 || ncols >= (1 << 30)) return false;
   const long long nnz = rp[nrows];
-  long long empties = 0;
+  long long empties = 0, extra_pieces = 0;
   for (int r = 0; r < nrows; ++r) {
     const int len = rp[r + 1] - rp[r];
-    if (len > SPMV3_MAXROW) return false;
+    if (len > SPMV3_MAXROW) {
+      if (!split_long) return false;
+      extra_pieces += (len + SPMV3_MAXROW - 1) / SPMV3_MAXROW - 1;
+    }
     if (len == 0) ++empties;
   }
+  if ((long long)nrows + extra_pieces > 2000000000LL) return false;
   const long long stored = nnz + empties;
   if (stored > 2000000000LL) return false;
   P.rowptr.resize((size_t)nrows + 1);
@@ -893,6 +955,15 @@ static bool spmv3_build_plan(int nrows, int ncols, const int *rp, const int *ci,
             out_v[pos] = va[k];
           }
           out_i[pos - 1] = (int)((unsigned)out_i[pos - 1] | SPMV3_END);
+          const int len = b - a;
+          if (len > SPMV3_MAXROW) {  // balanced pieces, an END after each of them
+            const int pieces = (len + SPMV3_MAXROW - 1) / SPMV3_MAXROW, small = len / pieces, big = len % pieces;
+            int e = orp[r];
+            for (int q = 0; q < pieces - 1; ++q) {
+              e += small + (q < big ? 1 : 0);
+              out_i[e - 1] = (int)((unsigned)out_i[e - 1] | SPMV3_END);
+            }
+          }
         }
       }
     };
@@ -921,17 +992,47 @@ static bool spmv3_build_plan(int nrows, int ncols, const int *rp, const int *ci,
       for (auto &x : th) x.join();
     }
   }
-  // warp-tiles: whole rows, aligned span (k0 & ~3 .. end) <= 128 entries
+  // virtual row pointers: identical to the row pointers unless a row was cut into pieces
+  std::vector<int> vrp_store;
+  const int *vrp = P.rowptr.data();
+  int nv = nrows;
+  P.vptr.clear();
+  P.nvrows = nrows;
+  if (extra_pieces > 0) {
+    nv = (int)(nrows + extra_pieces);
+    vrp_store.resize((size_t)nv + 1);
+    P.vptr.resize((size_t)nrows + 1);
+    int v = 0;
+    for (int r = 0; r < nrows; ++r) {
+      P.vptr[r] = v;
+      const int len = rp[r + 1] - rp[r];
+      if (len > SPMV3_MAXROW) {
+        const int pieces = (len + SPMV3_MAXROW - 1) / SPMV3_MAXROW, small = len / pieces, big = len % pieces;
+        int e = P.rowptr[r];
+        for (int q = 0; q < pieces; ++q) {
+          vrp_store[v++] = e;
+          e += small + (q < big ? 1 : 0);
+        }
+      } else {
+        vrp_store[v++] = P.rowptr[r];
+      }
+    }
+    P.vptr[nrows] = v;
+    vrp_store[v] = P.rowptr[nrows];
+    vrp = vrp_store.data();
+    P.nvrows = nv;
+  }
+  // warp-tiles: whole (virtual) rows, aligned span (k0 & ~3 .. end) <= 128 entries
   std::vector<int4> real;
   real.reserve((size_t)(stored / 100 + 16));
-  for (int r = 0; r < nrows;) {
-    const int k0 = P.rowptr[r], base = k0 & ~3;
+  for (int r = 0; r < nv;) {
+    const int k0 = vrp[r], base = k0 & ~3;
     int r1 = r;
-    while (r1 < nrows && P.rowptr[r1 + 1] - base <= SPMV3_WT) ++r1;
+    while (r1 < nv && vrp[r1 + 1] - base <= SPMV3_WT) ++r1;
     int4 t;
     t.x = r;
     t.y = k0;
-    t.z = P.rowptr[r1] - k0;
+    t.z = vrp[r1] - k0;
     t.w = r1 - r;
     real.push_back(t);
     r = r1;
@@ -968,7 +1069,8 @@ struct B200Spmv3PlanHost {
 extern "C" B200Spmv3PlanHost *b200_spmv3_plan_build(int nrows, int ncols, const int *rp, const int *ci,
                                                     const double *va, int grid_cap) {
   B200Spmv3PlanHost *h = new B200Spmv3PlanHost();
-  if (!spmv3_build_plan(nrows, ncols, rp, ci, va, grid_cap, h->plan)) {
+  const bool split = getenv("SCS_B200_SPMV_LONGROWS") != nullptr;
+  if (!spmv3_build_plan(nrows, ncols, rp, ci, va, grid_cap, h->plan, split)) {
     delete h;
     return nullptr;
   }
@@ -991,6 +1093,10 @@ extern "C" const int *b200_spmv3_plan_desc(const B200Spmv3PlanHost *h) {
   return reinterpret_cast<const int *>(h->plan.wt.data());
 }
 extern "C" const int *b200_spmv3_plan_cta_begin(const B200Spmv3PlanHost *h) { return h->plan.cta_begin.data(); }
+extern "C" int b200_spmv3_plan_nvrows(const B200Spmv3PlanHost *h) { return h->plan.nvrows; }
+extern "C" const int *b200_spmv3_plan_vptr(const B200Spmv3PlanHost *h) {
+  return h->plan.vptr.empty() ? nullptr : h->plan.vptr.data();
+}
 
 // ------------------------------------------------------------------ host side
 static int lanes_log2_for(int max_row_nnz) {
@@ -1046,6 +1152,13 @@ static int spmv_upload_v3(B200Spmv *M, const Spmv3Plan &P) {
   rc |= b200_h2d(M->d_vals, P.vals_data(), stored * 8);
   rc |= b200_h2d(M->d_wt3, P.wt.data(), P.wt.size() * sizeof(int4));
   rc |= b200_h2d(M->d_cta_begin3, P.cta_begin.data(), P.cta_begin.size() * 4);
+  M->nvrows = P.nvrows;
+  if (!P.vptr.empty()) {  // long-row mode
+    M->d_vptr = (int *)b200_malloc(P.vptr.size() * 4);
+    M->d_vscratch = (double *)b200_malloc((size_t)P.nvrows * 8);
+    if (!M->d_vptr || !M->d_vscratch) return -1;
+    rc |= b200_h2d(M->d_vptr, P.vptr.data(), P.vptr.size() * 4);
+  }
   rc |= b200_sync();  // the plan's host vectors go out of scope
   if (rc != 0) return -1;
   spmv_set_attrs();
@@ -1085,7 +1198,8 @@ extern "C" B200Spmv *b200_spmv_create(int nrows, int ncols, const int *h_rowptr,
     const char *ma = getenv("SCS_B200_SPMV_MINAVG");
     const bool too_short = ma && nrows > 0 && (double)nnz / nrows < atof(ma);
     Spmv3Plan P;
-    if (nrows > 0 && !too_short && spmv3_build_plan(nrows, ncols, h_rowptr, h_colidx, h_vals, cap, P)) {
+    const bool split_long = getenv("SCS_B200_SPMV_LONGROWS") != nullptr;  // staged: virtual rows + combine pass
+    if (nrows > 0 && !too_short && spmv3_build_plan(nrows, ncols, h_rowptr, h_colidx, h_vals, cap, P, split_long)) {
       if (spmv_upload_v3(M, P) != 0) {
         b200_spmv_destroy(M);
         return nullptr;
@@ -1236,6 +1350,8 @@ extern "C" void b200_spmv_destroy(B200Spmv *M) {
   b200_free(M->d_counter);
   b200_free(M->d_wt3);
   b200_free(M->d_cta_begin3);
+  b200_free(M->d_vptr);
+  b200_free(M->d_vscratch);
   free(M);
 }
 
@@ -1268,6 +1384,30 @@ extern "C" int b200_spmv(const B200Spmv *M, const B200SpmvArgs *a) {
     else if (M->version == 2) spmv_ws_kernel<POSTV><<<grid, block, smem, st>>>(ARGS);          \
     else spmv_csr_stream_kernel<POSTV><<<grid, block, smem, st>>>(ARGS);                       \
   } while (0)
+  if (M->version == 3 && M->d_vptr != nullptr) {
+    // staged long-row mode: sums per virtual row, then the combine pass with the real epilogue
+    spmv_flag_kernel<B200_POST_NONE><<<grid, block, smem, st>>>(
+        M->d_colidx, M->d_vals, M->d_wt3, M->d_cta_begin3, a->d_x, M->d_vscratch, nullptr, 1.0, nullptr, nullptr,
+        nullptr, B200_HOOK_NONE, nullptr, a->d_skip, M->d_partials, M->d_counter, 0ull);
+    int cg = (M->nrows + 255) / 256;
+    const int cap = 8 * b200_num_sms();
+    if (cg > cap) cg = cap;
+#define COMBINE(POSTV)                                                                                        \
+  spmv_combine_kernel<POSTV><<<cg, 256, 0, st>>>(M->nrows, M->d_vptr, M->d_vscratch, a->d_y, a->d_init,      \
+                                                 a->init_sign, a->d_d, a->d_v, a->d_dot, a->hook, a->d_hook_arg, \
+                                                 a->d_skip, M->d_partials, M->d_counter, a->hook_val)
+    switch (a->post) {
+      case B200_POST_NONE: COMBINE(B200_POST_NONE); break;
+      case B200_POST_DIV: COMBINE(B200_POST_DIV); break;
+      case B200_POST_FMA_DOT: COMBINE(B200_POST_FMA_DOT); break;
+      case B200_POST_FMA: COMBINE(B200_POST_FMA); break;
+      default: return -1;
+    }
+#undef COMBINE
+    b200_count_launch(2);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   switch (a->post) {
     case B200_POST_NONE: LAUNCH(B200_POST_NONE); break;
     case B200_POST_DIV: LAUNCH(B200_POST_DIV); break;

@@ -295,3 +295,53 @@ def test_plan_property_random_shapes(lib):
         assert np.abs(y - ref).max() <= 1e-13 * (np.abs(ref).max() + 1.0)
 
     check()
+
+
+def test_long_rows_as_virtual_rows(lib, monkeypatch):
+    """STAGED long-row mode (SCS_B200_SPMV_LONGROWS=1): rows longer than 124 entries are cut into balanced pieces
+    (an END flag per piece = one "virtual row"); the lane algorithm produces one sum per virtual row and the combine
+    pass (spmv_combine_kernel) adds the pieces of each true row in order."""
+    monkeypatch.setenv("SCS_B200_SPMV_LONGROWS", "1")
+    lib.b200_spmv3_plan_nvrows.restype = C.c_int
+    lib.b200_spmv3_plan_nvrows.argtypes = [C.c_void_p]
+    lib.b200_spmv3_plan_vptr.restype = C.POINTER(C.c_int)
+    lib.b200_spmv3_plan_vptr.argtypes = [C.c_void_p]
+    rng = np.random.default_rng(321)
+    for trial, (nrows, ncols, sampler) in enumerate([
+        (40, 3000, lambda: rng.choice([0, 3, 124, 125, 200, 248, 249, 700, 1500], 40)),
+        (300, 900, lambda: np.where(rng.random(300) < 0.1, rng.integers(125, 900, 300), rng.poisson(4, 300))),
+        (3, 2000, lambda: np.array([2000, 0, 1999])),
+    ]):
+        lens = np.minimum(sampler(), ncols)
+        rp, ci, va = random_csr(nrows, ncols, rng, lens)
+        ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+        lib.b200_spmv3_plan_build.restype = C.c_void_p
+        lib.b200_spmv3_plan_build.argtypes = [C.c_int, C.c_int, ip, ip, dp, C.c_int]
+        h = lib.b200_spmv3_plan_build(nrows, ncols, rp.ctypes.data_as(ip), ci.ctypes.data_as(ip), va.ctypes.data_as(dp), 5)
+        assert h
+        nv = lib.b200_spmv3_plan_nvrows(h)
+        vp = lib.b200_spmv3_plan_vptr(h)
+        pieces = np.maximum(1, -(-lens // MAXROW))
+        assert nv == pieces.sum()
+        vptr = np.ctypeslib.as_array(vp, (nrows + 1,)).copy() if (lens > MAXROW).any() else np.arange(nrows + 1)
+        assert np.array_equal(np.diff(vptr), pieces)
+        lib.b200_spmv3_plan_free(h)
+        plan = build_plan(lib, nrows, ncols, rp, ci, va, 5)
+        # format: CSR view unchanged, one END per virtual row, every piece <= 124 entries, pieces of a row balanced
+        is_end = (plan["idx"] & END) != 0
+        assert is_end.sum() == nv
+        assert np.array_equal(plan["rowptr"][1:] - plan["rowptr"][:-1], np.maximum(lens, 1))
+        ends = np.nonzero(is_end)[0]
+        plen = np.diff(np.concatenate([[-1], ends]))
+        assert plen.max() <= MAXROW
+        for r in np.nonzero(lens > MAXROW)[0]:
+            pl = plen[vptr[r]:vptr[r + 1]]
+            assert pl.sum() == lens[r] and pl.max() - pl.min() <= 1
+        real = plan["desc"][plan["desc"][:, 2] > 0]
+        assert real[-1, 0] + real[-1, 3] == nv and ((real[:, 1] + real[:, 2]) - (real[:, 1] & ~3) <= WT).all()
+        # lane algorithm on the virtual rows + combine
+        x = rng.standard_normal(ncols)
+        yv = emulate_kernel(plan, nv, x, rng)
+        y = np.array([yv[vptr[r]:vptr[r + 1]].sum() for r in range(nrows)])
+        ref = np.array([np.dot(va[rp[r]:rp[r + 1]], x[ci[rp[r]:rp[r + 1]]]) for r in range(nrows)])
+        assert np.abs(y - ref).max() <= 1e-12 * (np.abs(ref).max() + 1.0), trial

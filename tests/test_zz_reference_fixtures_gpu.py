@@ -153,3 +153,41 @@ def test_full_size_configs_are_self_consistent(lib, cfg, steps):
     assert np.abs(problems.proj_cone(s, prob["cone"]) - s).max() <= 1e-9 * smax
     ymax = max(1.0, np.abs(y).max())
     assert np.abs(problems.proj_dual_cone(y, prob["cone"]) - y).max() <= 1e-9 * ymax
+
+
+def test_long_row_mode_matches_reference(lib, reflib, monkeypatch):
+    """STAGED v3 long-row mode (virtual rows + combine pass, SCS_B200_SPMV_LONGROWS=1): both operators and a KKT
+    solve on matrices with 700-entry columns and 40-entry rows / very long rows."""
+    if not lib.scs_b200_device_ok():
+        pytest.skip("no sm_100 device")
+    monkeypatch.setenv("SCS_B200_SPMV_LONGROWS", "1")
+    from scs_b200 import problems
+    reflib._scs_accum_by_a.argtypes = [PP(capi.ScsMatrix), capi.c_double_p, capi.c_double_p]
+    reflib._scs_accum_by_atrans.argtypes = [PP(capi.ScsMatrix), capi.c_double_p, capi.c_double_p]
+    for m, n, col_nnz, seed in ((3000, 50, 700, 4), (64, 5000, 40, 5), (20000, 400, 300, 6)):
+        rng = np.random.default_rng(seed)
+        A = problems.random_sparse_csc(m, n, col_nnz, rng)
+        hp = capi.HostProblem(A, np.zeros(m), np.zeros(n), {"l": m})
+        dr = np.empty(n + m + 1)
+        dr[:n], dr[n:] = 1e-6, 10.0
+        w = lib.scs_init_lin_sys_work(C.byref(hp.A), None, capi.dptr(dr))
+        assert w
+        try:
+            x, yv = rng.standard_normal(n), rng.standard_normal(m)
+            mine, ref = np.zeros(m), np.zeros(m)
+            assert lib.scs_b200_accum_by_a(w, capi.dptr(x), capi.dptr(mine), 0) == 0
+            reflib._scs_accum_by_a(C.byref(hp.A), capi.dptr(x), capi.dptr(ref))
+            assert np.abs(mine - ref).max() / np.abs(ref).max() <= 1e-13
+            mine, ref = np.ones(n), np.ones(n)
+            assert lib.scs_b200_accum_by_atrans(w, capi.dptr(yv), capi.dptr(mine), 1) == 0
+            reflib._scs_accum_by_atrans(C.byref(hp.A), capi.dptr(yv), capi.dptr(ref))
+            assert np.abs(mine - ref).max() / np.abs(ref).max() <= 1e-13
+            rhs = rng.standard_normal(n + m)
+            wr = reflib.scs_init_lin_sys_work(C.byref(hp.A), None, capi.dptr(dr))
+            a, b = rhs.copy(), rhs.copy()
+            assert lib.scs_solve_lin_sys(w, capi.dptr(a), None, 1e-12) == 0
+            assert reflib.scs_solve_lin_sys(wr, capi.dptr(b), None, 1e-12) == 0
+            reflib.scs_free_lin_sys_work(wr)
+            assert np.abs(a - b).max() / np.abs(b).max() <= 1e-10
+        finally:
+            lib.scs_free_lin_sys_work(w)

@@ -1008,7 +1008,7 @@ extern "C" int b200_cg_solve(B200Cg *cg, double *d_b, const double *d_s, double 
   // (consecutive ADMM iterations need nearly the same number of CG steps), later batches are small.
   int batch = its_hint + (its_hint / 16 > 2 ? its_hint / 16 : 2);
   if (batch < 4) batch = 4;
-  if (batch > 4096) batch = 4096;
+  if (batch > 512) batch = 512;  // a sharp drop of the CG count between two solves wastes at most 512 empty iterations
   const int follow = its_hint / 8 > 8 ? (its_hint / 8 < 256 ? its_hint / 8 : 256) : 8;
   long long enq = 0;
   int polls = 0;

@@ -94,6 +94,7 @@ typedef struct B200CpsdCones B200CpsdCones;
 B200CpsdCones *b200_cpsd_create(int cssize, const int *h_cs, long long first_row);
 int b200_cpsd_project(B200CpsdCones *c, double *d_x, const double *d_s, const double *d_ry);
 void b200_cpsd_destroy(B200CpsdCones *c);
+void b200_cpsd_set_err(B200CpsdCones *c, int *d_err);
 int b200_cones_set_complex_psd(B200Cones *c, int cssize, const int *h_cs, int n_triples);
 void b200_cones_destroy(B200Cones *c);
 /* Projects the box/SOC/PSD rows. On entry d_x (length m, the y block of u) holds
@@ -103,6 +104,8 @@ int b200_cones_project_rest(B200Cones *c, double *d_x, const double *d_s, const 
 /* Full Moreau wrapper on a bare m-vector (operator-level tests): in place
  * x <- x + R^-1 Pi_K^{R^-1}(-R x); d_ry may be NULL (R = I). */
 int b200_cones_proj_dual(B200Cones *c, double *d_x, const double *d_ry);
+/* 0 unless a batched eigen-decomposition has reported info != 0 since creation (sticky); syncs */
+int b200_cones_check(B200Cones *c);
 double *b200_cones_scratch(B200Cones *c); /* m doubles (Moreau copy s) */
 
 /* ---------------------------------------------------------------- AA (kernels/aa.cu) */

@@ -30,6 +30,13 @@ long long b200_launches(void);
 /* CUDA-event timing on the library stream */
 int b200_timer_start(void);
 double b200_timer_stop_ms(void);       /* syncs; <0 on error */
+/* device-side section timers (ScsInfo.lin_sys_time / cone_time / accel_time): CUDA events on the library
+ * stream; the device time between two consecutive marks is billed to the section of the later mark */
+enum { B200_SEC_LINSYS = 0, B200_SEC_CONE = 1, B200_SEC_ACCEL = 2, B200_SEC_OTHER = 3 };
+int b200_section_begin(void);
+int b200_section_mark(int section);
+int b200_section_flush(void);          /* syncs with the last mark */
+double b200_section_ms(int section);
 
 /* ------------------------------------------------------------ SpMV ------- */
 /* A sparse operator stored row-major (CSR): row r has entries

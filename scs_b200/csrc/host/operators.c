@@ -80,7 +80,8 @@ scs_int scs_b200_proj_dual_cone(ScsB200ConeWork *c, scs_float *x, const scs_floa
   if (r_y && b200_h2d(c->d_ry, r_y, bytes) != 0) return -1;
   if (b200_cones_proj_dual(c->cones, c->d_x, r_y ? c->d_ry : SCS_NULL) != 0) return -1;
   if (b200_d2h(x, c->d_x, bytes) != 0) return -1;
-  return b200_sync() == 0 ? 0 : -1;
+  if (b200_sync() != 0) return -1;
+  return b200_cones_check(c->cones); /* a failed eigen-decomposition is an error, like cones.c:1048-1052 */
 }
 
 void scs_b200_finish_cone(ScsB200ConeWork *c) {

@@ -119,8 +119,9 @@ scs_int scs_b200_write_data(const char *filename, const ScsData *d, const ScsCon
   Stream s;
   const uint32_t head[3] = {(uint32_t)sizeof(int), (uint32_t)sizeof(double), (uint32_t)strlen(FILE_API_VERSION)};
   const uint32_t ext[2] = {EXT_MAGIC, 1u};
-  const int nbox = k->bsize > 1 ? k->bsize - 1 : 0;
+  int nbox;
   if (!filename || !d || !k || !stgs || !d->A) return -1;
+  nbox = k->bsize > 1 ? k->bsize - 1 : 0;
   s.f = fopen(filename, "wb");
   s.bad = 0;
   s.int_bytes = (int)sizeof(int);

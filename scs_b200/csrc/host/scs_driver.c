@@ -838,7 +838,7 @@ static void print_summary(ScsWork *w, int i, double t0) {
 /* ----------------------------------------------------------------- the solve */
 scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_int warm_start) {
   int i, l;
-  double t_solve, t0, total_accel = 0.0, total_cone = 0.0, total_lin = 0.0;
+  double t_solve, total_accel = 0.0, total_cone = 0.0, total_lin = 0.0;
   const long long launches0 = b200_launches();
   long long cg0, solves0;
   ScsSettings *stgs;
@@ -864,19 +864,20 @@ scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_int warm_star
     printf("\n");
   }
 
+  b200_section_begin();
   for (i = 0; i < stgs->max_iters; ++i) {
     const int check = (i % CONVERGED_INTERVAL == 0);
     int dual_done = 0;
     /* ---- Anderson acceleration (scs.c:1359-1366) */
     if (w->accel) {
       if (i > 0 && i % stgs->acceleration_interval == 0) {
-        t0 = now_ms();
+        b200_section_mark(B200_SEC_OTHER);
         w->aa_norm = b200_aa_apply_dev(w->accel, w->adm.d_v, w->adm.d_v_prev);
-        total_accel += now_ms() - t0;
+        b200_section_mark(B200_SEC_ACCEL);
       }
     }
     /* ---- normalize v, v_prev = v, u_t = R v, warm start, CG tolerance */
-    t0 = now_ms();
+    b200_section_mark(B200_SEC_OTHER);
     if (b200_admm_prep_linsys(&w->adm, i, w->accel != SCS_NULL, pow((double)i + 1, CG_RATE)) != 0)
       return failure(w, w->m, w->n, sol, info, SCS_FAILED, "error in project_lin_sys", "failure");
     /* ---- KKT solve (device PCG), tau from root_plus */
@@ -884,13 +885,13 @@ scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_int warm_star
       return failure(w, w->m, w->n, sol, info, SCS_FAILED, "error in project_lin_sys", "failure");
     if (b200_admm_root_plus(&w->adm, i) != 0)
       return failure(w, w->m, w->n, sol, info, SCS_FAILED, "error in project_lin_sys", "failure");
-    total_lin += now_ms() - t0;
+    b200_section_mark(B200_SEC_LINSYS);
     /* ---- cone projection */
-    t0 = now_ms();
     if (b200_admm_cone_pre(&w->adm, i, w->k->z, w->k->l, b200_cones_scratch(w->cones)) != 0 ||
         b200_cones_project_rest(w->cones, w->adm.d_u + w->n, b200_cones_scratch(w->cones),
                                 w->adm.d_R + w->n) != 0)
       return failure(w, w->m, w->n, sol, info, SCS_FAILED, "error in project_cones", "failure");
+    b200_section_mark(B200_SEC_CONE);
     /* ---- rsk (and, when nothing intervenes, the dual update in the same pass) */
     {
       const int fuse_dual = !check;
@@ -898,12 +899,11 @@ scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_int warm_star
         return failure(w, w->m, w->n, sol, info, SCS_FAILED, "error in compute_rsk", "failure");
       dual_done = fuse_dual;
     }
-    if (check) {
-      b200_sync();
-    }
-    total_cone += now_ms() - t0;
 
     if (check) {
+      b200_section_mark(B200_SEC_OTHER);
+      if (b200_section_flush() != 0 || b200_cones_check(w->cones) != 0)
+        return failure(w, w->m, w->n, sol, info, SCS_FAILED, "error in project_cones", "failure");
       if (populate_residual_struct(w, i) != 0)
         return failure(w, w->m, w->n, sol, info, SCS_FAILED, "error in residuals", "failure");
       if ((info->status_val = has_converged(w)) != 0) break;
@@ -927,12 +927,18 @@ scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_int warm_star
       return failure(w, w->m, w->n, sol, info, SCS_FAILED, "error in update_dual_vars", "failure");
     /* ---- AA safeguard (scs.c:1439-1447) */
     if (w->accel && i % stgs->acceleration_interval == 0 && w->aa_norm > 0) {
-      t0 = now_ms();
+      b200_section_mark(B200_SEC_OTHER);
       if (b200_aa_safeguard_dev(w->accel, w->adm.d_v, w->adm.d_v_prev) < 0) w->rejected_accel_steps++;
       else w->accepted_accel_steps++;
-      total_accel += now_ms() - t0;
+      b200_section_mark(B200_SEC_ACCEL);
     }
   }
+  b200_section_mark(B200_SEC_OTHER);
+  if (b200_section_flush() != 0 || b200_cones_check(w->cones) != 0)
+    return failure(w, w->m, w->n, sol, info, SCS_FAILED, "error in project_cones", "failure");
+  total_lin = b200_section_ms(B200_SEC_LINSYS);
+  total_cone = b200_section_ms(B200_SEC_CONE);
+  total_accel = b200_section_ms(B200_SEC_ACCEL);
   (void)l;
   if (stgs->verbose) {
     populate_residual_struct(w, i);

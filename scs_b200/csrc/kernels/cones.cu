@@ -78,7 +78,24 @@ struct B200Cones {
   long long tri_off;  // first row of the exponential triples
   double *d_pow;      // power cone parameters (sign = primal / dual), psize
   B200CpsdCones *cpsd;  // complex PSD blocks (kernels/cones_complex.cu; staged, see there), or NULL
+  // sticky device flag: OR of every per-matrix `info` the batched eigen-solver has returned (reference
+  // cones.c:1048-1052 propagates a failed syevr as "error in project_cones"); read by b200_cones_check
+  int *d_err;
 };
+
+// OR the eigen-solver's per-matrix status words into the sticky flag (tiny; runs after every batched syevd)
+__global__ void k_psd_info_or(int count, const int *__restrict__ info, int *err) {
+  int bad = 0;
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < count; b += gridDim.x * blockDim.x)
+    if (info[b] != 0) bad = 1;
+  if (bad) atomicOr(err, 1);
+}
+extern "C" void b200_psd_info_or(int count, const int *d_info, int *d_err) {
+  if (!d_err || count <= 0) return;
+  k_psd_info_or<<<(count + 255) / 256 > 64 ? 64 : (count + 255) / 256, 256, 0, (cudaStream_t)b200_stream()>>>(
+      count, d_info, d_err);
+  b200_count_launch(1);
+}
 
 // ------------------------------------------------------------------ SOC kernels
 __device__ __forceinline__ void soc_decide(double v1, double s, double &a0, double &scale) {
@@ -466,6 +483,8 @@ extern "C" B200Cones *b200_cones_create(int m, int nz, int nl, int bsize, const 
       b200_cones_destroy(c);
       return nullptr;
     }
+    c->d_err = (int *)b200_malloc(64);
+    if (!c->d_err || b200_memset0(c->d_err, 64) != 0) { b200_cones_destroy(c); return nullptr; }
     for (auto &kv : by_k) {
       const int k = kv.first;
       const int count = (int)kv.second.size();
@@ -484,7 +503,12 @@ extern "C" B200Cones *b200_cones_create(int m, int nz, int nl, int bsize, const 
       g.d_mats = (double *)b200_malloc((size_t)count * k * k * 8);
       g.d_evals = (double *)b200_malloc((size_t)count * k * 8);
       g.d_info = (int *)b200_malloc((size_t)count * 4);
-      if (!g.d_off || !g.d_mats || !g.d_evals || !g.d_info) { b200_cones_destroy(c); return nullptr; }
+      auto drop_group = [&]() {
+        b200_free(g.d_off); b200_free(g.d_mats); b200_free(g.d_evals); b200_free(g.d_info);
+        b200_free(g.d_work); free(g.h_work);
+        b200_cones_destroy(c);
+      };
+      if (!g.d_off || !g.d_mats || !g.d_evals || !g.d_info) { drop_group(); return nullptr; }
       rc |= b200_h2d(g.d_off, kv.second.data(), (size_t)count * 4);
       rc |= b200_sync();
       size_t wd = 0, wh = 0;
@@ -492,14 +516,14 @@ extern "C" B200Cones *b200_cones_create(int m, int nz, int nl, int bsize, const 
                                             CUBLAS_FILL_MODE_LOWER, k, CUDA_R_64F, g.d_mats, k,
                                             CUDA_R_64F, g.d_evals, CUDA_R_64F, &wd, &wh,
                                             count) != CUSOLVER_STATUS_SUCCESS) {
-        b200_cones_destroy(c);
+        drop_group();
         return nullptr;
       }
       g.work_bytes = wd;
       g.h_work_bytes = wh;
       g.d_work = b200_malloc(wd ? wd : 16);
       g.h_work = wh ? malloc(wh) : nullptr;
-      if (!g.d_work || (wh && !g.h_work)) { b200_cones_destroy(c); return nullptr; }
+      if (!g.d_work || (wh && !g.h_work)) { drop_group(); return nullptr; }
       c->groups->push_back(g);
     }
   }
@@ -516,6 +540,7 @@ extern "C" void b200_cones_destroy(B200Cones *c) {
   b200_free(c->d_big); b200_free(c->d_chunk_part); b200_free(c->d_head_a0); b200_free(c->d_psd1_off);
   b200_free(c->d_scratch);
   b200_free(c->d_pow);
+  b200_free(c->d_err);
   b200_cpsd_destroy(c->cpsd);
   if (c->groups) {
     for (auto &g : *c->groups) {
@@ -551,7 +576,12 @@ extern "C" int b200_cones_set_complex_psd(B200Cones *c, int cssize, const int *h
   if (rows == 0) return 0;
   const long long first = (long long)c->m - 3LL * n_triples - rows;
   if (first < 0) return -1;
+  if (!c->d_err) {
+    c->d_err = (int *)b200_malloc(64);
+    if (!c->d_err || b200_memset0(c->d_err, 64) != 0) return -1;
+  }
   c->cpsd = b200_cpsd_create(cssize, h_cs, first);
+  if (c->cpsd) b200_cpsd_set_err(c->cpsd, c->d_err);
   return c->cpsd ? 0 : -1;
 }
 
@@ -606,6 +636,7 @@ extern "C" int b200_cones_project_rest(B200Cones *c, double *d_x, const double *
         b200_set_error("cusolverDnXsyevBatched", cudaErrorUnknown, __FILE__, __LINE__);
         return -1;
       }
+      b200_psd_info_or(g.count, g.d_info, c->d_err);
       const int nt = (k + PT - 1) / PT;
       dim3 rg(nt, nt, g.count);
       k_psd_reconstruct<<<rg, PT * 8, 0, st>>>(k, g.count, g.d_off, g.d_mats, g.d_evals, d_x, d_s,
@@ -621,6 +652,19 @@ extern "C" int b200_cones_project_rest(B200Cones *c, double *d_x, const double *
       return -1;
   }
   CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// 0: every eigen-decomposition so far reported success; -1: at least one did not (sticky). Syncs the stream.
+extern "C" int b200_cones_check(B200Cones *c) {
+  if (!c || !c->d_err) return 0;
+  int h = 0;
+  if (b200_d2h(&h, c->d_err, sizeof(int)) != 0 || b200_sync() != 0) return -1;
+  if (h != 0) {
+    b200_set_error("batched syevd reported a failure (info != 0) in the PSD projection", cudaErrorUnknown, __FILE__,
+                   __LINE__);
+    return -1;
+  }
   return 0;
 }
 

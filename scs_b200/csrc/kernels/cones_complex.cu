@@ -149,7 +149,10 @@ struct B200CpsdCones {
   std::vector<CGroup> groups;
   cusolverDnHandle_t solver;
   cusolverDnParams_t params;
+  int *d_err;  // sticky "an eigen-decomposition failed" flag, owned by B200Cones (cones.cu)
 };
+extern "C" void b200_psd_info_or(int count, const int *d_info, int *d_err);  // cones.cu
+extern "C" void b200_cpsd_set_err(B200CpsdCones *c, int *d_err) { c->d_err = d_err; }
 
 extern "C" void b200_cpsd_destroy(B200CpsdCones *c) {
   if (!c) return;
@@ -230,6 +233,7 @@ extern "C" int b200_cpsd_project(B200CpsdCones *c, double *d_x, const double *d_
       return -1;
     }
     const int nt = (g.K + CPT - 1) / CPT;
+    b200_psd_info_or(g.count, g.d_info, c->d_err);
     dim3 rg(nt, nt, g.count);
     k_cpsd_reconstruct<<<rg, CPT * 8, 0, st>>>(g.kc, g.count, g.d_off, g.d_mats, g.d_evals, d_x, d_s, d_ry);
     b200_count_launch(2);

@@ -2,6 +2,7 @@
 // One process drives one GPU (LOCAL_RANK, overridable with SCS_B200_DEVICE).
 #include "../common.cuh"
 #include "../dev_api.h"
+#include <mutex>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -15,6 +16,15 @@ static char g_err[512] = "";
 static long long g_launches = 0;
 static void *g_stage = nullptr;  // pinned staging buffer for pageable host copies
 static size_t g_stage_bytes = 0;
+// Threading: the library drives ONE device through ONE stream. Calls may come from any host
+// thread -- every entry point that touches the device first binds the calling thread to that device
+// (cudaSetDevice is thread-local state) -- but they are serialised where they share state: the init, and the
+// pinned bounce buffer of the pageable-memory copies. Concurrent solves on the same stream are ordered by the
+// stream; include/scs_b200.h documents that one process = one GPU = one solve at a time.
+static std::mutex g_init_mu, g_stage_mu;
+static inline void bind_thread() {
+  if (g_init == 1) cudaSetDevice(g_dev);
+}
 
 extern "C" void b200_set_error(const char *what, cudaError_t e, const char *file, int line) {
   snprintf(g_err, sizeof(g_err), "%s:%d: %s -> %s", file, line, what, cudaGetErrorString(e));
@@ -25,7 +35,15 @@ extern "C" long long b200_launches(void) { return g_launches; }
 extern "C" const char *b200_last_error(void) { return g_err; }
 
 extern "C" int b200_runtime_init(void) {
-  if (g_init == 1) return 0;
+  if (g_init == 1) {
+    bind_thread();
+    return 0;
+  }
+  std::lock_guard<std::mutex> lk(g_init_mu);
+  if (g_init == 1) {
+    bind_thread();
+    return 0;
+  }
   if (g_init == -1) return -1;
   g_init = -1;
   int ndev = 0;
@@ -69,7 +87,9 @@ extern "C" void *b200_malloc(size_t bytes) {
   return p;
 }
 extern "C" void b200_free(void *p) {
-  if (p) cudaFree(p);
+  if (!p) return;
+  bind_thread();
+  cudaFree(p);
 }
 extern "C" void *b200_host_alloc(size_t bytes) {
   if (b200_runtime_init() != 0) return nullptr;
@@ -94,6 +114,7 @@ extern "C" int b200_h2d(void *d_dst, const void *src, size_t bytes) {
     CUDA_OK(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, g_stream));
     return 0;
   }
+  std::lock_guard<std::mutex> lk(g_stage_mu);
   size_t off = 0;
   while (off < bytes) {
     size_t c = bytes - off < g_stage_bytes ? bytes - off : g_stage_bytes;
@@ -114,6 +135,7 @@ extern "C" int b200_d2h(void *dst, const void *d_src, size_t bytes) {
     CUDA_OK(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, g_stream));
     return 0;
   }
+  std::lock_guard<std::mutex> lk(g_stage_mu);
   size_t off = 0;
   while (off < bytes) {
     size_t c = bytes - off < g_stage_bytes ? bytes - off : g_stage_bytes;
@@ -125,6 +147,7 @@ extern "C" int b200_d2h(void *dst, const void *d_src, size_t bytes) {
   return 0;
 }
 extern "C" int b200_d2d(void *d_dst, const void *d_src, size_t bytes) {
+  bind_thread();
   CUDA_OK(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, g_stream));
   return 0;
 }
@@ -148,4 +171,57 @@ extern "C" double b200_timer_stop_ms(void) {
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, g_ev0, g_ev1) != cudaSuccess) return -1.0;
   return (double)ms;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Section timers on the device (ScsInfo.lin_sys_time / cone_time / accel_time, reference semantics
+// src/scs.c:1360-1393,1472-1475 -- there a host clock around synchronous CPU code; here the work is
+// asynchronous, so the sections are bracketed by CUDA events ON THE LIBRARY STREAM and the elapsed device
+// time between consecutive marks is billed to the section named by the later mark).
+// b200_section_mark(s): "everything enqueued since the previous mark belongs to section s".
+// The marks of up to SEC_RING intervals are kept; b200_section_flush() (after any stream sync, e.g. at the
+// convergence check every 25 iterations) adds them up and recycles the events.
+#define SEC_RING 1024
+#define SEC_MAX 8
+static cudaEvent_t g_sec_ev[SEC_RING + 1];
+static int g_sec_tag[SEC_RING + 1];
+static int g_sec_n = 0;       // marks recorded since the last flush (event 0 = the open mark)
+static int g_sec_made = 0;
+static double g_sec_ms[SEC_MAX];
+extern "C" int b200_section_begin(void) {
+  bind_thread();
+  if (!g_sec_made) {
+    for (int i = 0; i <= SEC_RING; ++i) CUDA_OK(cudaEventCreate(&g_sec_ev[i]));
+    g_sec_made = 1;
+  }
+  for (int i = 0; i < SEC_MAX; ++i) g_sec_ms[i] = 0.0;
+  g_sec_n = 0;
+  CUDA_OK(cudaEventRecord(g_sec_ev[0], g_stream));
+  return 0;
+}
+extern "C" int b200_section_flush(void) {
+  if (!g_sec_made || g_sec_n == 0) return 0;
+  CUDA_OK(cudaEventSynchronize(g_sec_ev[g_sec_n]));
+  for (int i = 1; i <= g_sec_n; ++i) {
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, g_sec_ev[i - 1], g_sec_ev[i]));
+    g_sec_ms[g_sec_tag[i]] += (double)ms;
+  }
+  // the last mark opens the next interval
+  cudaEvent_t t = g_sec_ev[0];
+  g_sec_ev[0] = g_sec_ev[g_sec_n];
+  g_sec_ev[g_sec_n] = t;
+  g_sec_n = 0;
+  return 0;
+}
+extern "C" int b200_section_mark(int section) {
+  if (!g_sec_made || section < 0 || section >= SEC_MAX) return -1;
+  if (g_sec_n == SEC_RING && b200_section_flush() != 0) return -1;
+  ++g_sec_n;
+  g_sec_tag[g_sec_n] = section;
+  CUDA_OK(cudaEventRecord(g_sec_ev[g_sec_n], g_stream));
+  return 0;
+}
+extern "C" double b200_section_ms(int section) {
+  return (section >= 0 && section < SEC_MAX) ? g_sec_ms[section] : 0.0;
 }

@@ -1,31 +1,35 @@
 #!/usr/bin/env python
-"""bench.py -- ADMM iterations/sec of the SCS hot path on B200 (BASELINE.json metric).
+"""bench.py -- ADMM iterations/sec and time-to-eps of the SCS hot path on B200 (BASELINE.json metric).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2] [--scale f]
 
-A "step" is ONE ADMM iteration (normalise v -> indirect KKT solve by device PCG ->
-cone projection -> dual update, with Anderson acceleration every 10th step and the
-residual / scale check every 25th) on the synthetic workload named by `--config`
-(default C2: random sparse SOCP n=1e6, m=3e6, nnz=1e7, 50 SOC cones, fp64), run
-through the public C ABI (scs_init / scs_solve) of scs_b200/libscs_b200.so.
+A "step" is ONE ADMM iteration (normalise v -> indirect KKT solve by device PCG -> cone projection -> dual update,
+with Anderson acceleration every 10th step and the residual / scale check every 25th) on the synthetic workload
+named by `--config` (default C2: random sparse SOCP n=1e6, m=3e6, nnz=1e7, 50 SOC cones, fp64), run through the
+public C ABI (scs_init / scs_solve) of scs_b200/libscs_b200.so.
 
-  value  : K / (device-resident timed solve), problem already resident in HBM
-           (a warm-up solve of W iterations ran before; eps = 0 so exactly K
-           iterations execute).  CUDA events bracket the timed region; the
-           wall clock of the same region is printed too (they agree: the solve
-           synchronises at its end).
-  e2e    : K / wall time of the whole host-buffer call scs() = scs_init (H2D of A,
-           b, c; host equilibration) + scs_solve(K) + D2H of (x, y, s) + scs_finish.
-  roofline: the SpMV kernels (dominant: ~78 % of the algorithmic bytes of a CG
-           iteration), timed live with CUDA events, alternating A x and A'y so
-           that the 2 x 124 MB of matrix data never sit in the 126 MB L2.
-  cpu_baseline: the UNMODIFIED reference CPU-indirect solver (oracle/_ref, all host
-           threads via its OpenMP build) on a bounded sample of the same workload.
+BOTH ARMS TIME THE SAME WINDOW: the first K ADMM iterations of a COLD-STARTED solve with default settings and
+eps = 0 (so exactly K iterations run) -- identical algorithmic work, identical `config` dict.
 
---impl reference times that same reference solver as the whole arm.
-N > 1: one process per GPU, ONE cooperative solve of the same workload (strong scaling): A is
-row-sharded across the ranks, x-space vectors are replicated, the only data-path collective is
-an NCCL all-reduce of the n-vector per CG iteration (+ one all-gather of y per KKT solve).
+  value  : K / (device-resident cold solve of K iterations), problem already resident in HBM, after W untimed
+           warm-up iterations on the same workspace.  CUDA events bracket the timed region; the wall clock of the
+           same region is printed too (they agree: the solve synchronises at its end).
+  e2e    : K / wall time of the whole host-buffer call scs() = scs_init (H2D of A, b, c; transpose, SpMV plans,
+           equilibration) + scs_solve(K) + D2H of (x, y, s) + scs_finish.
+  time_to_eps_1e-4 : the other half of BASELINE's metric -- a separate default-settings solve to eps_abs =
+           eps_rel = 1e-4 (status, iterations, setup and solve seconds, residuals); the CPU reference needs hours
+           for this, its figure is an extrapolation from its measured iterations/s and labelled so.
+  roofline: the kernels of the CG loop AS THEY RUN IN THE SOLVE (spmv_flag_kernel<POST_DIV> on the solver's own p,
+           <POST_FMA_DOT>+alpha hook on its tmp, k_cg_update, k_cg_pupdate), each bracketed by CUDA events inside
+           genuine CG iterations; consecutive kernels stream 2 x 124 MB of matrix data, more than the 126 MB L2.
+  parity : the gates of SURVEY 8(d) measured in this very run: our first 3 ADMM iterations against the reference's
+           (the cpu_baseline sample), relative differences of x, y, s and the ScsInfo residuals.
+  cpu_baseline: the UNMODIFIED reference CPU-indirect solver (oracle/_ref, OpenMP build) on a bounded sample (the
+           first 3 iterations) of the same workload.
+
+--impl reference times that same reference solver for the same K cold iterations as the whole arm.
+N > 1: one process per GPU, ONE cooperative solve of the same workload (strong scaling): A is row-sharded across the
+ranks; per CG iteration the partial products are summed by a fused kernel over NVLink peer memory.
 """
 import argparse
 import ctypes as C
@@ -103,6 +107,16 @@ def measured_peak_gbs():
     return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s"
 
 
+def workload_config(name, scale, n, m, nnz, steps):
+    """The `config` dict: identical in both arms (same generator, seed, sizes, settings and iteration window)."""
+    return {"workload": f"{name}: {CONFIG_DESC.get(name, '')}", "scale": scale, "n": int(n), "m": int(m),
+            "nnz": int(nnz), "generator": "scs_b200/problems.py config(), seed 1234",
+            "settings": "SCS defaults (AA mem 10 / interval 10, adaptive scale, normalize), eps = 0 so exactly K "
+                        "iterations run",
+            "window": f"ADMM iterations 1..{int(steps)} of a cold-started solve",
+            "l2": "working set (A and A' = 2 x 124 MB at C2, streamed alternately, + vectors) exceeds the 126 MB L2"}
+
+
 def build_problem(name, scale, seed):
     from scs_b200 import problems
     t0 = time.time()
@@ -151,6 +165,9 @@ def _reference_worker():
     ref.scs_solve(w, C.byref(sol), C.byref(info), 0)
     t_solve = time.time() - t0
     ref.scs_finish(w)
+    if spec.get("dump"):
+        np.savez(spec["dump"], x=x, y=y, s=s, info=np.array([info.pobj, info.dobj, info.res_pri, info.res_dual,
+                                                               info.gap]))
     print("REFRESULT " + json.dumps({
         "iters": int(info.iter), "solve_s": t_solve, "init_s": t_init, "its_per_s": info.iter / t_solve,
         "e2e_its_per_s": info.iter / (t_solve + t_init), "lin_sys_ms": info.lin_sys_time,
@@ -158,12 +175,12 @@ def _reference_worker():
         "nnz": prob["nnz"]}))
 
 
-def run_reference(args, iters, lib, omp_threads, blas_threads=1):
+def run_reference(args, iters, lib, omp_threads, blas_threads=1, dump=None):
     env = dict(os.environ)
     env["OMP_NUM_THREADS"] = str(omp_threads)
     env["OPENBLAS_NUM_THREADS"] = str(blas_threads)
     env["SCS_REF_WORKER"] = json.dumps({"config": args.config, "scale": args.scale, "seed": args.seed,
-                                        "iters": int(iters), "lib": lib})
+                                        "iters": int(iters), "lib": lib, "dump": dump})
     env.pop("RANK", None)
     p = subprocess.run([sys.executable, os.path.abspath(__file__)], env=env, capture_output=True, text=True)
     for line in p.stdout.splitlines():
@@ -174,7 +191,7 @@ def run_reference(args, iters, lib, omp_threads, blas_threads=1):
     raise RuntimeError("reference worker failed: " + p.stderr[-500:])
 
 
-def best_reference(args, iters, probe_iters=2):
+def best_reference(args, iters, probe_iters=2, dump=None):
     """The reference with 'all the host threads it can use'. Only accum_by_atrans is parallel in the
     reference (OpenMP, linsys/scs_matrix.c:174-176); probing on this pool's hosts (profiles/README.md: 1, 8,
     32, 128 threads) showed 32 threads fastest and all 128 hardware threads 6x SLOWER, so the default is
@@ -187,7 +204,7 @@ def best_reference(args, iters, probe_iters=2):
     ncores = os.cpu_count() or 1
     if not os.environ.get("SCS_BENCH_PROBE"):
         lib, t = (omp, min(32, ncores)) if os.path.exists(omp) else (plain, 1)
-        r = run_reference(args, iters, lib, t, 1)
+        r = run_reference(args, iters, lib, t, 1, dump=dump)
         r["cores"] = t
         r["probes"] = "not probed (SCS_BENCH_PROBE=1 to probe; earlier probes: profiles/README.md)"
         return r
@@ -205,20 +222,27 @@ def best_reference(args, iters, probe_iters=2):
         return None
     best = max(probes, key=lambda r: r["its_per_s"])
     lib = plain if best["lib"] == os.path.basename(plain) else omp
-    r = run_reference(args, iters, lib, best["omp_threads"], best["blas_threads"]) if iters > probe_iters else best
+    r = run_reference(args, iters, lib, best["omp_threads"], best["blas_threads"], dump=dump) \
+        if (iters > probe_iters or dump) else best
     r["cores"] = best["omp_threads"]
     r["probes"] = [{"lib": q["lib"], "threads": q["omp_threads"], "its_per_s": q["its_per_s"]} for q in probes]
     return r
 
 
 def ncu_traffic(kernel_key):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-    (profiles/spmv_ncu_traffic.json, written from gpurun_out by scripts/ncu_summary.py), or None."""
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the named in-loop kernel from the
+    committed `ncu --set full` capture (profiles/spmv_ncu_traffic.json, written from gpurun_out by
+    scripts/ncu_summary.py), or None. ncu cannot run inside a timed bench: this is the one number of the line that is
+    read from a file, and the file names the capture it came from."""
     p = os.path.join(ROOT, "profiles", "spmv_ncu_traffic.json")
     try:
         return float(json.load(open(p))[kernel_key]["dram_bytes_per_launch"])
     except Exception:
         return None
+
+
+def rel_err(a, b):
+    return float(np.abs(a - b).max() / max(1.0, float(np.abs(b).max())))
 
 
 def main():
@@ -231,6 +255,7 @@ def main():
     ap.add_argument("--scale", type=float, default=float(os.environ.get("SCS_BENCH_SCALE", "1.0")))
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tte", action="store_true", help="skip the time-to-eps solve")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -250,29 +275,29 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        # bounded sample: a reference iteration of C2 takes ~10 s on this pool's hosts, so K is capped
-        # (SCS_BENCH_REF_ITERS) to keep the arm within a few minutes; small configs run all K steps
+        # the SAME window as our arm: K cold iterations of the full workload. One reference iteration of C2 takes
+        # ~10 s on this pool's hosts (32 OpenMP threads), i.e. ~3.5 min at the driver's K = 20; SCS_BENCH_REF_ITERS
+        # caps K for larger requests (the line then says steps_run < steps).
+        cap = int(os.environ.get("SCS_BENCH_REF_ITERS", "25"))
         big = args.scale >= 0.5 and args.config != "C1"
-        k = int(min(args.steps, int(os.environ.get("SCS_BENCH_REF_ITERS", "6")))) if big else int(args.steps)
-        k = max(k, 2)
+        k = max(2, int(min(args.steps, cap)) if big else int(args.steps))
         r = best_reference(args, k)
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}))
             return 0
-        probe = {"probes": r["probes"]}
-        prob = {"n": r["n"], "m": r["m"], "nnz": r["nnz"]}
         out = dict(base)
         out.update({
             "impl": "reference", "value": r["its_per_s"], "ms_per_step": 1e3 / r["its_per_s"], "n_gpus": world,
-            "steps_run": r["iters"],
-            "config": {"workload": f"{args.config}: {CONFIG_DESC.get(args.config, '')}", "scale": args.scale,
-                       "n": prob["n"], "m": prob["m"], "nnz": prob["nnz"], "settings": "SCS defaults, eps=0"},
+            "steps": int(r["iters"]), "steps_requested": args.steps,
+            "config": workload_config(args.config, args.scale, r["n"], r["m"], r["nnz"], args.steps),
             "cpu_baseline": {"value": r["its_per_s"], "unit": "iters/s", "cores": r["cores"], "kind": "reference",
-                             "sample": f"{r['iters']} ADMM iterations of the unmodified reference CPU-indirect "
+                             "sample": f"{r['iters']} cold ADMM iterations of the unmodified reference CPU-indirect "
                                        f"solver ({r['lib']}, OMP_NUM_THREADS={r['cores']}; thread choice: "
-                                       f"{probe['probes']}) on the full workload"},
+                                       f"{r['probes']}) on the full workload"},
             "e2e": {"value": r["e2e_its_per_s"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
+            "lin_sys_ms": r["lin_sys_ms"], "cone_ms": r["cone_ms"], "accel_ms": r["accel_ms"],
+            "setup_ms": 1e3 * r["init_s"],
         })
         print(json.dumps(out))
         return 0
@@ -304,7 +329,6 @@ def main():
     n, m, nnz = prob["n"], prob["m"], prob["nnz"]
     eps0 = dict(eps_abs=0.0, eps_rel=0.0, eps_infeas=0.0)
 
-    # ---- e2e: whole host-buffer call (init + K iterations + finish), copies inside the timed region
     def barrier():
         if world > 1:
             dist.barrier()
@@ -314,6 +338,8 @@ def main():
     # buffer are one-time process costs, not part of a solve (the reference arm has no such cold start)
     w0, _, _ = run_solver(lib, capi, hp, dict(max_iters=3, **eps0))
     lib.scs_finish(w0)
+
+    # ---- e2e: whole host-buffer call (init + K cold iterations + finish), copies inside the timed region
     barrier()
     t0 = time.time()
     w, info_e, sols = run_solver(lib, capi, hp, dict(max_iters=args.steps, **eps0))
@@ -323,7 +349,7 @@ def main():
     h2d = nnz * 12 + (n + 1) * 4 + (m + n) * 8          # A (vals+idx+ptr), b, c
     d2h = (n + 2 * m) * 8                                # x, y, s
 
-    # ---- device-resident: init once, W warm-up steps, then exactly K timed steps (warm-started)
+    # ---- device-resident: init once, W warm-up steps, then exactly K timed steps of a COLD-STARTED solve
     st = capi.default_settings(lib, verbose=0, max_iters=args.warmup, **eps0)
     w = lib.scs_init(C.byref(hp.data), C.byref(hp.cone), C.byref(st))
     if not w:
@@ -339,7 +365,7 @@ def main():
     launches0 = lib.scs_b200_launch_count()
     t0 = time.time()
     ev0.record()
-    lib.scs_solve(w, C.byref(sol), C.byref(info), 1)
+    lib.scs_solve(w, C.byref(sol), C.byref(info), 0)          # cold start: the same window as the reference arm
     ev1.record()
     barrier()
     wall_s = time.time() - t0
@@ -351,16 +377,24 @@ def main():
     iters = int(info.iter)
     lib.scs_finish(w)
 
-    # ---- optional (SCS_BENCH_TTE=1): time to the default stopping criterion eps_abs = eps_rel = 1e-4, the second
-    # half of BASELINE.json's metric; a separate full solve so that the K-step timing above is untouched
+    # ---- time to the default stopping criterion eps_abs = eps_rel = 1e-4 (second half of BASELINE's metric):
+    # a separate full solve so that the K-step timing above is untouched
     tte = None
-    if os.environ.get("SCS_BENCH_TTE"):
-        w2, info_t, _ = run_solver(lib, capi, hp, dict(max_iters=100000))
+    want_tte = not args.no_tte and os.environ.get("SCS_BENCH_TTE", "1") != "0"
+    if want_tte:
+        t0 = time.time()
+        w2, info_t, sol_t = run_solver(lib, capi, hp, dict(max_iters=100000))
         lib.scs_finish(w2)
         tte = {"status": info_t.status.decode(errors="replace"), "iters": int(info_t.iter),
-               "solve_s": info_t.solve_time / 1e3, "setup_s": info_t.setup_time / 1e3, "pobj": info_t.pobj,
+               "solve_s": info_t.solve_time / 1e3, "setup_s": info_t.setup_time / 1e3,
+               "wall_s_incl_init_and_copies": time.time() - t0, "pobj": info_t.pobj,
                "known_optimum": prob.get("opt"), "res_pri": info_t.res_pri, "res_dual": info_t.res_dual,
-               "gap": info_t.gap}
+               "gap": info_t.gap, "lin_sys_s": info_t.lin_sys_time / 1e3, "cone_s": info_t.cone_time / 1e3,
+               "accel_s": info_t.accel_time / 1e3}
+        if world > 1:
+            tm = torch.tensor([tte["solve_s"], tte["setup_s"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            tte["solve_s"], tte["setup_s"] = float(tm[0]), float(tm[1])
 
     # max over ranks / sum of work
     tmax = solve_s
@@ -371,12 +405,13 @@ def main():
     value = iters / tmax             # ONE cooperative solve: the job's iterations / slowest rank
     e2e_value = args.steps / e2e_s
 
-    # ---- roofline of the dominant kernels, timed live with CUDA events (rank 0)
+    # ---- roofline of the in-loop kernels, timed live with CUDA events inside genuine CG iterations
     roof = None
     extra = {}
     cpu_base = None
-    if True:  # every rank takes part (the sharded workspace init is collective); rank 0 reports
-        peak, peak_src = measured_peak_gbs()
+    parity = None
+    peak, peak_src = measured_peak_gbs()
+    if world == 1:
         dr = np.empty(n + m + 1)
         z = int(prob["cone"].get("z", 0))
         dr[:n] = 1e-6
@@ -384,65 +419,88 @@ def main():
         dr[n + z:n + m] = 10.0
         dr[n + m] = 10.0
         lw = lib.scs_init_lin_sys_work(C.byref(hp.A), None, capi.dptr(dr))
-        ab = C.c_double(0.0)
-        rows = []
-        for op, name in ((0, "spmv_flag_kernel<POST_NONE> y=A x (rows of A)"),
-                         (1, "spmv_flag_kernel<POST_NONE> y=A'x (columns of A)")):
-            ms = lib.scs_b200_time_spmv(lw, op, 20, C.byref(ab))
-            rows.append({"kernel": name, "ms": ms, "alg_bytes": ab.value, "achieved": ab.value / ms / 1e6,
-                         "frac": ab.value / ms / 1e6 / peak})
-        ms_cg = lib.scs_b200_time_cg_iter(lw, 50, C.byref(ab))
-        cg_row = {"kernel": "one CG iteration (K1 A p, K2 A' z + dot, K3 update, K4 p)", "ms": ms_cg,
-                  "alg_bytes": ab.value, "achieved": ab.value / ms_cg / 1e6, "frac": ab.value / ms_cg / 1e6 / peak}
+        rhs = np.concatenate([prob["c"], prob["b"]])
+        ms = (C.c_double * 5)()
+        by = (C.c_double * 5)()
+        rc = lib.scs_b200_time_cg_kernels(lw, capi.dptr(rhs), 50, ms, by)
         lib.scs_free_lin_sys_work(lw)
-        dom = max(rows, key=lambda r: r["ms"])
-        roof = {"bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
-                "traffic": ncu_traffic("A x" if dom is rows[0] else "A'x") if (args.config == "C2" and args.scale == 1.0 and world == 1) else None,
-                "kernel": dom["kernel"], "ms_per_launch": dom["ms"],
-                "alg_bytes_per_launch": dom["alg_bytes"], "peak_source": peak_src,
-                "l2_flush": "alternating A / A' launches: 2 x matrix bytes > L2"}
-        extra["roofline_all"] = rows + [cg_row]
-        if not args.no_cpu_baseline and world == 1:
+        if rc == 0:
+            names = ["K1 spmv_flag_kernel<POST_DIV>: tmp = R_y^-1 (A p)  [rows of A, gathers p]",
+                     "K2 spmv_flag_kernel<POST_FMA_DOT>+alpha hook: Gp = R_x p + A' tmp, p'Gp  [columns of A, gathers tmp]",
+                     "K3 k_cg_update: x += a p, r -= a Gp, z = M r, z'r, |r|_inf, beta",
+                     "K4 k_cg_pupdate: p = z + beta p",
+                     "one CG iteration (K1..K4, launch gaps included)"]
+            rows = [{"kernel": names[k], "ms": ms[k], "alg_bytes": by[k], "achieved": by[k] / ms[k] / 1e6,
+                     "frac": by[k] / ms[k] / 1e6 / peak} for k in range(5)]
+            dom = max(rows[:4], key=lambda r: r["ms"])
+            key = "K1" if dom is rows[0] else ("K2" if dom is rows[1] else None)
+            roof = {"bound": "hbm", "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                    "traffic": ncu_traffic(key) if (key and args.config == "C2" and args.scale == 1.0) else None,
+                    "traffic_source": "profiles/spmv_ncu_traffic.json (ncu --set full capture of the same kernel)",
+                    "kernel": dom["kernel"], "ms_per_launch": dom["ms"], "alg_bytes_per_launch": dom["alg_bytes"],
+                    "peak_source": peak_src,
+                    "timing": "CUDA events around every launch inside 50 genuine CG iterations on the solver's own "
+                              "vectors (rhs = [c; b]); K1 / K2 alternate, so each streams its 124 MB matrix after "
+                              "the other's 124 MB passed through the 126 MB L2",
+                    "share_of_cg_iteration": dom["ms"] / ms[4]}
+            extra["roofline_all"] = rows
+        if not args.no_cpu_baseline:
             try:
                 k = (3 if args.config != "C1" else 40) if args.scale >= 0.5 else 40
-                r = best_reference(args, k)
+                dump = os.path.join("/tmp", f"scs_bench_ref_{os.getpid()}.npz")
+                r = best_reference(args, k, dump=dump)
                 if r:
                     cpu_base = {"value": r["its_per_s"], "unit": "iters/s", "cores": r["cores"], "kind": "reference",
-                                "sample": f"{r['iters']} ADMM iterations of the unmodified reference CPU-indirect "
-                                          f"solver ({r['lib']}, {r['cores']} threads; thread choice: {r['probes']}) on the same "
-                                          f"workload (setup {r['init_s']:.1f}s excluded)"}
+                                "sample": f"the first {r['iters']} cold ADMM iterations of the unmodified reference "
+                                          f"CPU-indirect solver ({r['lib']}, {r['cores']} threads; thread choice: "
+                                          f"{r['probes']}) on the same workload (setup {r['init_s']:.1f}s excluded)"}
+                    # parity gate of SURVEY 8(d), measured in this run: our first k iterations vs the reference's
+                    if os.path.exists(dump):
+                        g = np.load(dump)
+                        wq, iq, sq = run_solver(lib, capi, hp, dict(max_iters=int(r["iters"]), **eps0))
+                        lib.scs_finish(wq)
+                        mine = [iq.pobj, iq.dobj, iq.res_pri, iq.res_dual, iq.gap]
+                        parity = {"window": f"first {r['iters']} ADMM iterations, cold start, vs the reference run of "
+                                            "cpu_baseline (max-norm relative differences; iterations >= 2 solve the "
+                                            "KKT system only to the adaptive CG tolerance)",
+                                  "x": rel_err(sq[0], g["x"]), "y": rel_err(sq[1], g["y"]), "s": rel_err(sq[2], g["s"])}
+                        for nm, a, b in zip(("pobj", "dobj", "res_pri", "res_dual", "gap"), mine, g["info"]):
+                            parity[nm] = abs(a - b) / max(1.0, abs(b))
+                        os.remove(dump)
             except Exception as e:  # the checker must never break the measurement
                 cpu_base = {"value": None, "unit": "iters/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
 
     if rank == 0:
         out = dict(base)
         out.update({
-            "value": value, "ms_per_step": 1e3 * tmax / max(iters, 1),
-            "config": {"workload": f"{args.config}: {CONFIG_DESC.get(args.config, '')}", "scale": args.scale,
-                       "n": n, "m": m, "nnz": nnz, "settings": "SCS defaults (AA mem 10, adaptive scale), eps=0 so "
-                       "exactly K iterations run", "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: A row-sharded by nnz-balanced row "
-                       "blocks, x-space replicated; per CG iteration the partial A_g'z (n doubles) of every rank is "
-                       "summed by a fused kernel reading the peers over NVLink (CUDA IPC; NCCL all-reduce fallback)",
-                       "l2": "working set (A, A' = 2 x 124 MB + vectors) exceeds the 126 MB L2"},
+            "value": value, "ms_per_step": 1e3 * tmax / max(iters, 1), "steps": iters,
+            "config": workload_config(args.config, args.scale, n, m, nnz, args.steps),
+            "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: A row-sharded by nnz-balanced row "
+            "blocks, x-space replicated; per CG iteration the partial A_g'z (n doubles) of every rank is "
+            "summed by a fused kernel reading the peers over NVLink (CUDA IPC; NCCL all-reduce fallback)",
             "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": h2d / args.steps,
                     "d2h_bytes_per_step": d2h / args.steps,
-                    "note": "whole scs() on host buffers: scs_init (host transpose + SpMV plans, H2D, device equilibration) + K iterations + D2H; one untimed 3-iteration call ran before (process cold start)"},
+                    "note": "whole scs() on host buffers: scs_init (transpose + SpMV plans, H2D, device equilibration) + K cold iterations + D2H; one untimed 3-iteration call ran before (process cold start)"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "cg_iters_per_step": stats.cg_iters / max(iters, 1),
             "timed_wall_s": wall_s, "timed_device_event_s": ev0.elapsed_time(ev1) / 1e3,
             "lin_sys_ms": info.lin_sys_time, "cone_ms": info.cone_time, "accel_ms": info.accel_time,
-            "setup_ms": info.setup_time, "problem_gen_s": gen_s,
+            "info_timers": "CUDA events on the solver's stream (device time per section)",
+            "setup_ms": info_e.setup_time, "problem_gen_s": gen_s,
         })
         if tte:
             # the CPU reference needs hours for this: its time is extrapolated from its measured iterations/s
             if cpu_base and cpu_base.get("value"):
                 tte["cpu_reference_extrapolated_s"] = tte["iters"] / cpu_base["value"]
+                tte["cpu_reference_note"] = "EXTRAPOLATION: our iteration count / the reference's measured iterations/s"
             out["time_to_eps_1e-4"] = tte
         if roof:
             out["roofline"] = roof
         if cpu_base:
             out["cpu_baseline"] = cpu_base
+        if parity:
+            out["parity"] = parity
         out.update(extra)
         print(json.dumps(out))
     if world > 1:

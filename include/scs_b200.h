@@ -178,6 +178,13 @@ double scs_b200_time_spmv(ScsLinSysWork *w, scs_int op, scs_int reps,
                           double *alg_bytes);
 /* Time `reps` CG iterations (4 kernels each) the same way. */
 double scs_b200_time_cg_iter(ScsLinSysWork *w, scs_int reps, double *alg_bytes);
+/* The kernels of the CG loop AS THEY RUN INSIDE A SOLVE (the solver's own p / tmp / r after a genuine CG start
+ * on the host right-hand side b, length n+m), each bracketed by CUDA events on the library stream:
+ * out_ms[0..4] = ms per launch of K1 (tmp = R_y^-1 A p), K2 (Gp = R_x p + A' tmp, p'Gp, alpha), K3 (x, r, z update
+ * + reductions), K4 (p update) and of the whole iteration; out_bytes[0..4] = algorithmic bytes of each
+ * (reference path: linsys/cpu/indirect/private.c:106-119,174-214). Single GPU, P = NULL. 0 on success. */
+scs_int scs_b200_time_cg_kernels(ScsLinSysWork *w, const scs_float *b, scs_int reps, double *out_ms,
+                                 double *out_bytes);
 
 /* Cone operator: replaces reference src/cones.c:1498-1596 (init_cone /
  * proj_dual_cone / finish_cone) for zero, LP, box, SOC, PSD, exponential and power cones.

@@ -224,6 +224,8 @@ def _declare(lib, ours):
     lib.scs_b200_time_spmv.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p]
     lib.scs_b200_time_cg_iter.restype = C.c_double
     lib.scs_b200_time_cg_iter.argtypes = [C.c_void_p, C.c_int, c_double_p]
+    lib.scs_b200_time_cg_kernels.restype = C.c_int
+    lib.scs_b200_time_cg_kernels.argtypes = [C.c_void_p, c_double_p, C.c_int, c_double_p, c_double_p]
     lib.scs_b200_init_cone.restype = C.c_void_p
     lib.scs_b200_init_cone.argtypes = [C.POINTER(ScsCone), C.c_int, c_double_p]
     lib.scs_b200_proj_dual_cone.restype = C.c_int

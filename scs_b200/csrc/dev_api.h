@@ -130,6 +130,8 @@ int b200_cg_solve(B200Cg *cg, double *d_b, const double *d_s, double tol, int ma
 /* one CG iteration (4 kernels), for timing */
 int b200_cg_one_iteration(B200Cg *cg, double *d_x);
 double b200_cg_iter_alg_bytes(const B200Cg *cg);
+/* per-kernel device times (ms per launch) of `reps` genuine CG iterations: K1, K2, K3, K4, whole iteration */
+int b200_cg_time_kernels(B200Cg *cg, double *d_x, int reps, double *out_ms);
 
 /* ------------------------------------------------------------ comm (kernels/comm.cu) */
 int b200_comm_rank(void);

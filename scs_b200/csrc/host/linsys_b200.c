@@ -481,6 +481,34 @@ double scs_b200_time_spmv(ScsLinSysWork *w, scs_int op, scs_int reps, double *al
   return ms[op == 0 ? 0 : 1];
 }
 
+/* bench.py roofline: the kernels of the CG loop as they run inside a solve (the solver's own p / tmp / r after
+ * a genuine start on the right-hand side b, which the caller provides: length n + m, host). out_ms[0..4] = ms
+ * per launch of K1, K2, K3, K4 and of the whole iteration; out_bytes[0..4] = the algorithmic bytes of each
+ * (K1 12 nnz + 4(m+1) + 8n + 16m, K2 12 nnz + 4(n+1) + 8m + 24n, K3 64n, K4 24n). */
+scs_int scs_b200_time_cg_kernels(ScsLinSysWork *w, const scs_float *b, scs_int reps, double *out_ms,
+                                 double *out_bytes) {
+  const size_t nm = (size_t)w->n + w->m;
+  const double nnz = (double)b200_spmv_nnz(w->A), n = (double)w->n, m = (double)w->m;
+  int k;
+  if (w->nranks > 1 || w->P) return -1;
+  if (b200_h2d(w->d_b, b, nm * 8) != 0) return -1;
+  if (b200_cg_solve(&w->cg, w->d_b, NULL, 0.0, 1, 0, NULL) < 0) return -1; /* genuine start: p, r, z, ctl */
+  w->cg.h_ctl->done = 0;
+  w->cg.h_ctl->max_its = 2000000000;
+  if (b200_h2d(w->cg.d_ctl, w->cg.h_ctl, sizeof(B200CgCtl)) != 0) return -1;
+  for (k = 0; k < 3; ++k) if (b200_cg_one_iteration(&w->cg, w->d_b) != 0) return -1;
+  if (b200_sync() != 0) return -1;
+  if (b200_cg_time_kernels(&w->cg, w->d_b, (int)reps, out_ms) != 0) return -1;
+  if (out_bytes) {
+    out_bytes[0] = 12.0 * nnz + 4.0 * (m + 1.0) + 8.0 * n + 16.0 * m;
+    out_bytes[1] = 12.0 * nnz + 4.0 * (n + 1.0) + 8.0 * m + 24.0 * n;
+    out_bytes[2] = 64.0 * n;
+    out_bytes[3] = 24.0 * n;
+    out_bytes[4] = b200_cg_iter_alg_bytes(&w->cg);
+  }
+  return 0;
+}
+
 double scs_b200_time_cg_iter(ScsLinSysWork *w, scs_int reps, double *alg_bytes) {
   /* run `reps` genuine CG iterations on a synthetic rhs with the stop test
    * disabled (tol = 0 never satisfies ||r|| < tol) and time them on the stream */

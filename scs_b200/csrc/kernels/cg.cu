@@ -960,6 +960,67 @@ static int cg_iteration(B200Cg *cg, double *d_x) {
 
 extern "C" int b200_cg_one_iteration(B200Cg *cg, double *d_x) { return cg_iteration(cg, d_x); }
 
+// Per-kernel device times of the CG loop AS IT RUNS IN A SOLVE (bench.py roofline): `reps` genuine iterations on
+// the solver's own p / tmp / r, every kernel bracketed by CUDA events on the library stream. out_ms[0..3] = average
+// per launch of K1 (tmp = R_y^-1 A p, spmv POST_DIV), K2 (Gp = R_x p + A' tmp, p'Gp, alpha: spmv POST_FMA_DOT + hook),
+// K3 (k_cg_update), K4 (k_cg_pupdate); out_ms[4] = whole iteration (first event to last, launch gaps included).
+// Single-GPU, P = NULL path only (the configuration the roofline is quoted on).
+extern "C" int b200_cg_time_kernels(B200Cg *cg, double *d_x, int reps, double *out_ms) {
+  if (cg->nranks > 1 || cg->P || reps <= 0) return -1;
+  cudaStream_t st = (cudaStream_t)b200_stream();
+  const int n = cg->n;
+  int g = (n + VEC_THREADS * 8 - 1) / (VEC_THREADS * 8);
+  if (g > 2 * b200_num_sms()) g = 2 * b200_num_sms();
+  if (g < 1) g = 1;
+  std::vector<cudaEvent_t> ev((size_t)reps * 5);
+  for (auto &e : ev) e = nullptr;
+  int rc = -1;
+  bool ok = true;
+  for (auto &e : ev)
+    if (cudaEventCreate(&e) != cudaSuccess) ok = false;
+  if (ok) {
+    const int *d_skip = &cg->d_ctl->done;
+    for (int r = 0; r < reps && ok; ++r) {
+      B200SpmvArgs a;
+      memset(&a, 0, sizeof(a));
+      cudaEventRecord(ev[(size_t)r * 5 + 0], st);
+      a.d_x = cg->d_p; a.d_y = cg->d_tmp; a.init_sign = 1.0; a.post = B200_POST_DIV; a.d_d = cg->d_ry;
+      a.d_skip = d_skip;
+      if (b200_spmv(cg->A, &a) != 0) ok = false;
+      cudaEventRecord(ev[(size_t)r * 5 + 1], st);
+      a.d_x = cg->d_tmp; a.d_y = cg->d_Gp; a.post = B200_POST_FMA_DOT; a.d_d = cg->d_rx; a.d_v = cg->d_p;
+      a.d_dot = &cg->d_ctl->pGp; a.hook = B200_HOOK_CG_ALPHA; a.d_hook_arg = cg->d_ctl;
+      if (b200_spmv(cg->At, &a) != 0) ok = false;
+      cudaEventRecord(ev[(size_t)r * 5 + 2], st);
+      k_cg_update<<<g, VEC_THREADS, 0, st>>>(n, d_x, cg->d_r, cg->d_p, cg->d_Gp, cg->d_M, cg->d_z, cg->d_ctl,
+                                             cg->d_partials, cg->d_counter);
+      cudaEventRecord(ev[(size_t)r * 5 + 3], st);
+      k_cg_pupdate<<<g, VEC_THREADS, 0, st>>>(n, cg->d_p, cg->d_z, cg->d_ctl);
+      cudaEventRecord(ev[(size_t)r * 5 + 4], st);
+      b200_count_launch(2);
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) ok = false;
+  }
+  if (ok) {
+    for (int k = 0; k < 5; ++k) out_ms[k] = 0.0;
+    for (int r = 0; r < reps; ++r) {
+      for (int k = 0; k < 4; ++k) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[(size_t)r * 5 + k], ev[(size_t)r * 5 + k + 1]);
+        out_ms[k] += ms;
+      }
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[(size_t)r * 5], ev[(size_t)r * 5 + 4]);
+      out_ms[4] += ms;
+    }
+    for (int k = 0; k < 5; ++k) out_ms[k] /= reps;
+    rc = 0;
+  }
+  for (auto &e : ev)
+    if (e) cudaEventDestroy(e);
+  return rc;
+}
+
 extern "C" double b200_cg_iter_alg_bytes(const B200Cg *cg) {
   const double nnz = (double)b200_spmv_nnz(cg->A);
   return 24.0 * nnz + 4.0 * (cg->m + cg->n + 2.0) + 24.0 * cg->m + 120.0 * cg->n;

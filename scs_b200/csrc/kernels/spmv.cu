@@ -4,26 +4,19 @@
 // A'x on the CSC arrays and A x on the explicit transpose) and the cuSPARSE
 // calls of linsys/gpu/gpu.c:3-58.
 //
-// Design ("CSR-stream" on TMA):
-//   * the nonzeros are cut into TILES of consecutive whole rows holding at most
-//     tile_nnz (<=2048) entries; a row longer than a tile is cut into chunks
-//     that stay on one CTA (running carry);
-//   * each CTA owns a contiguous, weight-balanced range of tiles (static
-//     partition => no atomics, bit-reproducible) and walks it with a 3-stage
-//     ring: one elected thread issues 1-D TMA bulk copies (cp.async.bulk,
-//     L2 evict_first) of the tile's value and column-index slices into shared
-//     memory, completion signalled on an mbarrier;
-//   * phase 1: all threads gather x[col] for the tile's entries (coalesced reads
-//     of idx from smem, up to 4 independent 8-byte gathers per thread in flight)
-//     and store the rounded products val*x[col] in shared memory;
-//   * phase 2: L lanes per row (L=1 for short rows) add the row's products IN
-//     STORAGE ORDER -- for L=1 this is the same sequential multiply-then-add chain
-//     as the reference's scalar loop `yj += Ax[p] * x[Ai[p]]` (which gcc does not
-//     contract to fma in the oracle build, checked with objdump), so the result
-//     is bit-identical to the CPU; L>1 finishes with a fixed xor-shuffle tree;
-//   * fused epilogues: y = s | s / d[r] | fma(d[r], v[r], s) plus the dot
-//     product v'y with a deterministic last-block reduction and an optional
-//     hook that turns the dot into the CG step length on the device.
+// Two kernels (history and sweeps: profiles/README.md):
+//   * v3 "flagged stream" (spmv_flag_kernel, the default): nonzero-per-lane on a TMA ring, rows recovered from
+//     END flags with ballots and a segmented warp scan -- see the block comment above the kernel. Rows longer
+//     than a warp-tile are cut into "virtual rows" whose partial sums a second, tiny pass adds in order
+//     (spmv_combine_kernel), so v3 serves every operator;
+//   * v2 "warp-specialised row-per-lane" (spmv_ws_kernel): kept as the fallback for operators v3 cannot plan
+//     (dimension / size limits) and for A/B measurements (SCS_B200_SPMV=2).
+// Both: static CTA partition (no atomics => a launch is bit-reproducible), 1-D TMA bulk copies
+// (cp.async.bulk, L2 evict_first) of the value / index slices into shared memory with mbarrier completion,
+// products rounded separately from the adds (__dmul_rn / __dadd_rn: the reference's scalar loop
+// `yj += Ax[p] * x[Ai[p]]` is not contracted to fma in the oracle build), fused epilogues
+// y = s | s / d[r] | fma(d[r], v[r], s) plus the dot product v'y with a deterministic last-block reduction and
+// an optional hook that turns the dot into the CG step length on the device.
 //
 // Algorithmic bytes per launch: 12*nnz + 4*(R+1) + 8*C + 8*R (+8*R per
 // extra row vector read by the epilogue).
@@ -39,26 +32,8 @@ extern "C" int b200_host_threads(long long work_items);  // host/linsys_b200.c
 
 // tuning knobs (overridable with -D for sweeps; see profiles/README.md for the measurements)
 #ifndef SPMV_DEFAULT_VERSION
-#define SPMV_DEFAULT_VERSION 3  // flagged stream (SCS_B200_SPMV=2: warp-specialised row-per-lane, =1: two-phase)
+#define SPMV_DEFAULT_VERSION 3  // flagged stream (SCS_B200_SPMV=2 forces the warp-specialised row-per-lane kernel)
 #endif
-#ifndef SPMV_THREADS
-#define SPMV_THREADS 512
-#endif
-#ifndef SPMV_STAGES
-#define SPMV_STAGES 3
-#endif
-#ifndef SPMV_TILE_NNZ
-#define SPMV_TILE_NNZ 2048
-#endif
-#ifndef SPMV_CTAS_PER_SM
-#define SPMV_CTAS_PER_SM 2
-#endif
-#define SPMV_TILE_CAP (SPMV_TILE_NNZ + 8)
-#ifndef SPMV_TILE_ROWS
-#define SPMV_TILE_ROWS (SPMV_TILE_NNZ / 2)
-#endif
-#define SPMV_GATHERS (SPMV_TILE_NNZ / SPMV_THREADS)  // independent gathers per thread in flight
-
 // tile descriptor: x=row0, y=nrows | (type<<28) | (lg_lanes<<24), z=k0, w=nnz
 #define TILE_NORMAL 0
 #define TILE_LONG_FIRST 1
@@ -79,34 +54,15 @@ struct B200Spmv {
   int tile_nnz;
   double *d_partials;
   unsigned int *d_counter;
-  int version;  // 1: two-phase block kernel, 2: warp-specialised pipeline, 3: flagged stream
+  int version;  // 2: warp-specialised row-per-lane pipeline (fallback), 3: flagged stream
   long long stored;  // entries held in d_colidx / d_vals (v3: nnz + one explicit zero per empty row)
   int4 *d_wt3;       // v3 warp-tile descriptors, padded per CTA to groups of SPMV3_NCW
   int *d_cta_begin3; // v3: first group of every CTA
-  // STAGED long-row support (SCS_B200_SPMV_LONGROWS=1): virtual rows + combine pass, see Spmv3Plan::vptr
+  // long-row support: virtual rows + combine pass, see Spmv3Plan::vptr
   int nvrows;        // virtual rows (== nrows when no row was cut)
   int *d_vptr;       // nrows+1, or NULL
   double *d_vscratch;  // nvrows partial sums
 };
-
-static size_t spmv_smem_bytes() {
-  return (size_t)SPMV_STAGES * SPMV_TILE_CAP * 8 + (size_t)SPMV_TILE_NNZ * 8 +
-         (size_t)SPMV_STAGES * SPMV_TILE_CAP * 4 + SPMV_STAGES * 8 + 64 * 8 +
-         (size_t)(SPMV_TILE_ROWS + 8) * 4;
-}
-
-__device__ __forceinline__ void spmv_issue_tile(const int4 t, int stage, double *s_vals, int *s_idx,
-                                                uint64_t *s_bar, const double *__restrict__ vals,
-                                                const int *__restrict__ colidx, uint64_t pol) {
-  const int k0 = t.z, nnz = t.w;
-  const int ka = k0 & ~3;
-  const int cnt = (k0 + nnz - ka + 3) & ~3;
-  mbar_expect_tx(&s_bar[stage], (unsigned)cnt * 12u);
-  if (cnt > 0) {
-    tma_load_1d(s_vals + (size_t)stage * SPMV_TILE_CAP, vals + ka, (unsigned)cnt * 8u, &s_bar[stage], pol);
-    tma_load_1d(s_idx + (size_t)stage * SPMV_TILE_CAP, colidx + ka, (unsigned)cnt * 4u, &s_bar[stage], pol);
-  }
-}
 
 // random 8-byte gather of the dense vector: read-only path, optionally without L1 allocation
 __device__ __forceinline__ double gather_ld(const double *p) {
@@ -151,180 +107,6 @@ __device__ __forceinline__ double spmv_epilogue(double s, int row, double *__res
   }
   y[row] = out;
   return out;
-}
-
-template <int POST>
-__global__ void __launch_bounds__(SPMV_THREADS, SPMV_CTAS_PER_SM)
-spmv_csr_stream_kernel(const int *__restrict__ rowptr, const int *__restrict__ colidx,
-                       const double *__restrict__ vals, const int4 *__restrict__ tiles,
-                       const int *__restrict__ cta_tile_begin, const double *__restrict__ x,
-                       double *__restrict__ y, const double *init, double init_sign,
-                       const double *__restrict__ d, const double *__restrict__ v, double *dot_out,
-                       int hook, void *hook_arg, const int *skip, double *partials,
-                       unsigned int *counter, unsigned long long hook_val) {
-  if (skip != nullptr && *((volatile const int *)skip) != 0) return;
-
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *s_vals = reinterpret_cast<double *>(smem_raw);
-  double *s_xg = s_vals + SPMV_STAGES * SPMV_TILE_CAP;
-  int *s_idx = reinterpret_cast<int *>(s_xg + SPMV_TILE_NNZ);
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_idx + SPMV_STAGES * SPMV_TILE_CAP);
-  double *s_red = reinterpret_cast<double *>(s_bar + SPMV_STAGES);
-  int *s_rp = reinterpret_cast<int *>(s_red + 64);  // row pointers of the current tile
-
-  const int tid = threadIdx.x;
-  const int t_begin = cta_tile_begin[blockIdx.x];
-  const int nt = cta_tile_begin[blockIdx.x + 1] - t_begin;
-  uint64_t pol = 0;
-
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < SPMV_STAGES; ++s) mbar_init(&s_bar[s], 1);
-    mbar_fence_init();
-    pol = l2_policy_evict_first();
-  }
-  __syncthreads();
-  if (tid == 0) {
-    const int pre = nt < SPMV_STAGES ? nt : SPMV_STAGES;
-    for (int s = 0; s < pre; ++s)
-      spmv_issue_tile(tiles[t_begin + s], s, s_vals, s_idx, s_bar, vals, colidx, pol);
-  }
-
-  double dot_acc = 0.0;
-  double carry = 0.0;  // long-row running sum (thread 0)
-
-  for (int i = 0; i < nt; ++i) {
-    const int st = i % SPMV_STAGES;
-    const unsigned par = (unsigned)((i / SPMV_STAGES) & 1);
-    const int4 t = tiles[t_begin + i];
-    const int row0 = t.x;
-    const int nrows = t.y & 0x00ffffff;
-    const int lg = (t.y >> 24) & 0xf;
-    const int type = (t.y >> 28) & 0x7;
-    const int k0 = t.z, nnz = t.w;
-    const int off = k0 - (k0 & ~3);
-    const double *__restrict__ tv = s_vals + (size_t)st * SPMV_TILE_CAP + off;
-    const int *__restrict__ ti = s_idx + (size_t)st * SPMV_TILE_CAP + off;
-
-    mbar_wait(&s_bar[st], par);
-
-    // ---- phase 1: stage the tile's row pointers, then gather x for every entry. All of a
-    // thread's loads are issued before any is consumed (SPMV_GATHERS independent 8-byte gathers
-    // in flight per thread): the L1 wavefront rate, not the latency, should bound this phase.
-    {
-      constexpr int RPL = SPMV_TILE_ROWS / SPMV_THREADS + 1;
-      int rpv[RPL];
-      int c[SPMV_GATHERS];
-      double xv[SPMV_GATHERS];
-      if (type == TILE_NORMAL) {
-#pragma unroll
-        for (int u = 0; u < RPL; ++u) {
-          const int r = tid + u * SPMV_THREADS;
-          rpv[u] = (r <= nrows) ? __ldg(&rowptr[row0 + r]) : 0;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < SPMV_GATHERS; ++u) {
-        const int k = tid + u * SPMV_THREADS;
-        c[u] = (k < nnz) ? ti[k] : -1;
-      }
-#pragma unroll
-      for (int u = 0; u < SPMV_GATHERS; ++u) xv[u] = (c[u] >= 0) ? __ldg(&x[c[u]]) : 0.0;
-      if (type == TILE_NORMAL) {
-#pragma unroll
-        for (int u = 0; u < RPL; ++u) {
-          const int r = tid + u * SPMV_THREADS;
-          if (r <= nrows) s_rp[r] = rpv[u] - k0;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < SPMV_GATHERS; ++u) {
-        const int k = tid + u * SPMV_THREADS;
-        if (k < nnz) s_xg[k] = __dmul_rn(tv[k], xv[u]);
-      }
-    }
-    __syncthreads();
-
-    // ---- phase 2: per-row FMA chains
-    if (type == TILE_NORMAL) {
-      if (lg == 0) {
-        for (int r = tid; r < nrows; r += SPMV_THREADS) {
-          const int row = row0 + r;
-          const int a = s_rp[r], b = s_rp[r + 1];
-          double s = (init != nullptr) ? init_sign * init[row] : 0.0;
-          for (int k = a; k < b; ++k) s = __dadd_rn(s, s_xg[k]);
-          spmv_epilogue<POST>(s, row, y, d, v, dot_acc);
-        }
-      } else {
-        const int L = 1 << lg;
-        const int group = tid >> lg, lig = tid & (L - 1), ngroups = SPMV_THREADS >> lg;
-        const int npass = (nrows + ngroups - 1) / ngroups;
-        for (int pass = 0; pass < npass; ++pass) {
-          const int r = pass * ngroups + group;
-          const bool valid = r < nrows;
-          const int row = row0 + (valid ? r : 0);
-          int a = 0, b = 0;
-          if (valid) {
-            a = s_rp[r];
-            b = s_rp[r + 1];
-          }
-          double s = 0.0;
-          for (int k = a + lig; k < b; k += L) s = __dadd_rn(s, s_xg[k]);
-          for (int o = L >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          if (valid && lig == 0) {
-            if (init != nullptr) s += init_sign * init[row];
-            spmv_epilogue<POST>(s, row, y, d, v, dot_acc);
-          }
-        }
-      }
-    } else {
-      // chunk of one long row: whole block reduces, thread 0 carries across chunks
-      double part[1] = {0.0};
-      for (int k = tid; k < nnz; k += SPMV_THREADS) part[0] = __dadd_rn(part[0], s_xg[k]);
-      block_sum<1>(part, s_red);
-      if (tid == 0) {
-        if (type == TILE_LONG_FIRST || type == TILE_LONG_ONLY)
-          carry = (init != nullptr) ? init_sign * init[row0] : 0.0;
-        carry += part[0];
-        if (type == TILE_LONG_LAST || type == TILE_LONG_ONLY)
-          spmv_epilogue<POST>(carry, row0, y, d, v, dot_acc);
-      }
-    }
-    __syncthreads();  // stage st and s_xg are free again
-    if (tid == 0 && i + SPMV_STAGES < nt)
-      spmv_issue_tile(tiles[t_begin + i + SPMV_STAGES], st, s_vals, s_idx, s_bar, vals, colidx, pol);
-  }
-
-  if (hook == B200_HOOK_P2P_SIGNAL) {
-    // multi-GPU: tell every peer that this rank's partial product is complete (last block only)
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      const unsigned tk = atomicAdd(counter, 1u);
-      if (tk == gridDim.x - 1) {
-        *counter = 0u;
-        __threadfence_system();
-        const B200P2pSignal *ps = reinterpret_cast<const B200P2pSignal *>(hook_arg);
-        for (int r = 0; r < ps->nranks; ++r)
-          if (r != ps->rank) *((volatile unsigned long long *)(ps->flags[r] + ps->rank)) = hook_val;
-      }
-    }
-  }
-
-  if (POST == B200_POST_FMA_DOT) {
-    double acc[1] = {dot_acc};
-    block_sum<1>(acc, s_red);
-    if (grid_finish<1>(acc, partials, counter, 0u, s_red)) {
-      if (tid == 0) {
-        *dot_out = acc[0];
-        if (hook == B200_HOOK_CG_ALPHA) {
-          B200CgCtl *c = reinterpret_cast<B200CgCtl *>(hook_arg);
-          c->pGp = acc[0];
-          c->alpha = c->ztr / acc[0];
-        }
-      }
-    }
-  }
 }
 
 // ==================================================================================
@@ -834,7 +616,7 @@ spmv_flag_kernel(const int *__restrict__ colidx, const double *__restrict__ vals
 }
 
 
-// STAGED (not yet run on hardware): second pass of the long-row mode. The flag kernel has written one sum per
+// Second pass of the long-row mode. The flag kernel has written one sum per
 // VIRTUAL row into `part`; thread r adds the pieces of true row r in order, applies the epilogue and the same
 // deterministic dot / hook tail as the one-pass kernels.
 template <int POST>
@@ -900,7 +682,7 @@ struct Spmv3Plan {
   std::vector<int> cta_begin;  // grid+1, in groups of SPMV3_NCW descriptors
   int grid = 0;
   int nwt = 0;               // real warp-tiles
-  // STAGED long-row support: a row longer than SPMV3_MAXROW is cut into pieces ("virtual rows", an END flag at
+  // long-row support: a row longer than SPMV3_MAXROW is cut into pieces ("virtual rows", an END flag at
   // the end of every piece); the kernel then produces one sum per virtual row and a combine pass adds the
   // pieces of each true row. vptr[r] = first virtual row of true row r (empty when no row was cut).
   std::vector<int> vptr;
@@ -1069,7 +851,8 @@ struct B200Spmv3PlanHost {
 extern "C" B200Spmv3PlanHost *b200_spmv3_plan_build(int nrows, int ncols, const int *rp, const int *ci,
                                                     const double *va, int grid_cap) {
   B200Spmv3PlanHost *h = new B200Spmv3PlanHost();
-  const bool split = getenv("SCS_B200_SPMV_LONGROWS") != nullptr;
+  const char *lr = getenv("SCS_B200_SPMV_LONGROWS");
+  const bool split = !(lr && atoi(lr) == 0);
   if (!spmv3_build_plan(nrows, ncols, rp, ci, va, grid_cap, h->plan, split)) {
     delete h;
     return nullptr;
@@ -1116,7 +899,6 @@ static void spmv_set_attrs() {
     cudaFuncSetAttribute(K<B200_POST_FMA_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES)); \
     cudaFuncSetAttribute(K<B200_POST_FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES));     \
   } while (0)
-  SET_ATTR(spmv_csr_stream_kernel, spmv_smem_bytes());
   SET_ATTR(spmv_ws_kernel, spmv2_smem_bytes());
   SET_ATTR(spmv_flag_kernel, spmv3_smem_bytes());
 #undef SET_ATTR
@@ -1186,7 +968,7 @@ extern "C" B200Spmv *b200_spmv_create(int nrows, int ncols, const int *h_rowptr,
   {
     const char *e = getenv("SCS_B200_SPMV");
     M->version = e ? atoi(e) : SPMV_DEFAULT_VERSION;
-    if (M->version < 1 || M->version > 3) M->version = SPMV_DEFAULT_VERSION;
+    if (M->version < 2 || M->version > 3) M->version = SPMV_DEFAULT_VERSION;
   }
   if (M->version == 3) {
     // flagged stream; operators with a row longer than SPMV3_MAXROW keep the plain CSR + v2 kernel
@@ -1198,7 +980,10 @@ extern "C" B200Spmv *b200_spmv_create(int nrows, int ncols, const int *h_rowptr,
     const char *ma = getenv("SCS_B200_SPMV_MINAVG");
     const bool too_short = ma && nrows > 0 && (double)nnz / nrows < atof(ma);
     Spmv3Plan P;
-    const bool split_long = getenv("SCS_B200_SPMV_LONGROWS") != nullptr;  // staged: virtual rows + combine pass
+    // rows longer than a warp-tile: virtual rows + combine pass (SCS_B200_SPMV_LONGROWS=0 sends such operators
+    // to the v2 kernel instead; first hardware run: profiles/r02a_first_call.log)
+    const char *lr = getenv("SCS_B200_SPMV_LONGROWS");
+    const bool split_long = !(lr && atoi(lr) == 0);
     if (nrows > 0 && !too_short && spmv3_build_plan(nrows, ncols, h_rowptr, h_colidx, h_vals, cap, P, split_long)) {
       if (spmv_upload_v3(M, P) != 0) {
         b200_spmv_destroy(M);
@@ -1210,14 +995,14 @@ extern "C" B200Spmv *b200_spmv_create(int nrows, int ncols, const int *h_rowptr,
   }
   // tile size: full tiles for big matrices, smaller ones so that small matrices
   // still spread over all SMs
-  const int max_tile = M->version == 2 ? SPMV2_TILE_NNZ : SPMV_TILE_NNZ;
-  const int ctas_per_sm = M->version == 2 ? SPMV2_CTAS_PER_SM : SPMV_CTAS_PER_SM;
+  const int max_tile = SPMV2_TILE_NNZ;
+  const int ctas_per_sm = SPMV2_CTAS_PER_SM;
   long long want = nnz / (2LL * ctas_per_sm * nsm);
   int tile_nnz = 256 < max_tile ? 256 : max_tile;
   while (tile_nnz < max_tile && tile_nnz < want) tile_nnz <<= 1;
   if (tile_nnz > max_tile) tile_nnz = max_tile;
   M->tile_nnz = tile_nnz;
-  const int tile_rows = M->version == 2 ? SPMV2_TILE_ROWS : SPMV_TILE_ROWS;
+  const int tile_rows = SPMV2_TILE_ROWS;
 
   std::vector<int4> tiles;
   tiles.reserve((size_t)(nnz / tile_nnz + nrows / tile_rows + 16));
@@ -1369,9 +1154,8 @@ extern "C" double b200_spmv_alg_bytes(const B200Spmv *M, int extra_row_vectors) 
 extern "C" int b200_spmv(const B200Spmv *M, const B200SpmvArgs *a) {
   if (M->nrows == 0) return 0;
   cudaStream_t st = (cudaStream_t)b200_stream();
-  const size_t smem = M->version == 3 ? spmv3_smem_bytes()
-                                      : (M->version == 2 ? spmv2_smem_bytes() : spmv_smem_bytes());
-  dim3 grid(M->grid), block(M->version == 3 ? SPMV3_THREADS : (M->version == 2 ? SPMV2_THREADS : SPMV_THREADS));
+  const size_t smem = M->version == 3 ? spmv3_smem_bytes() : spmv2_smem_bytes();
+  dim3 grid(M->grid), block(M->version == 3 ? SPMV3_THREADS : SPMV2_THREADS);
 #define TAIL                                                                                   \
   a->d_x, a->d_y, a->d_init, a->init_sign, a->d_d, a->d_v, a->d_dot, a->hook, a->d_hook_arg,   \
       a->d_skip, M->d_partials, M->d_counter, a->hook_val
@@ -1381,11 +1165,10 @@ extern "C" int b200_spmv(const B200Spmv *M, const B200SpmvArgs *a) {
     if (M->version == 3)                                                                       \
       spmv_flag_kernel<POSTV><<<grid, block, smem, st>>>(M->d_colidx, M->d_vals, M->d_wt3,     \
                                                          M->d_cta_begin3, TAIL);               \
-    else if (M->version == 2) spmv_ws_kernel<POSTV><<<grid, block, smem, st>>>(ARGS);          \
-    else spmv_csr_stream_kernel<POSTV><<<grid, block, smem, st>>>(ARGS);                       \
+    else spmv_ws_kernel<POSTV><<<grid, block, smem, st>>>(ARGS);                               \
   } while (0)
   if (M->version == 3 && M->d_vptr != nullptr) {
-    // staged long-row mode: sums per virtual row, then the combine pass with the real epilogue
+    // long-row mode: sums per virtual row, then the combine pass with the real epilogue
     spmv_flag_kernel<B200_POST_NONE><<<grid, block, smem, st>>>(
         M->d_colidx, M->d_vals, M->d_wt3, M->d_cta_begin3, a->d_x, M->d_vscratch, nullptr, 1.0, nullptr, nullptr,
         nullptr, B200_HOOK_NONE, nullptr, a->d_skip, M->d_partials, M->d_counter, 0ull);

@@ -32,8 +32,8 @@ def pytest_sessionstart(session):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
-    config.addinivalue_line("markers", "gpu_unverified: needs a real B200 and has NOT been run on one yet (written after the "
-                            "round's GPU budget was spent); promote to `gpu` after the first green run: -m gpu_unverified")
+    config.addinivalue_line("markers", "gpu_unverified: needs a real B200 and has NOT been run on one yet; promote to `gpu` "
+                            "after the first green run (none at present: round 1's were promoted in round 2)")
 
 
 @pytest.fixture(scope="session")

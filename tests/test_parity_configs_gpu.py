@@ -1,0 +1,191 @@
+"""Solver-level parity on the BASELINE.json configurations C2..C5 (scaled so that the CPU reference finishes in
+seconds), the full-size C2 KKT solve, and the C4-sized PSD batch -- all against the UNMODIFIED reference
+(oracle/_ref, travels with the tree) through the C ABI.  VERDICT r01 "next round" item 1.
+
+Gates, printed with every run:
+  * one ADMM iteration (max_iters=1: equilibration, KKT solve at tol 1e-12, cone projection, un-normalisation):
+    x, y, s and pobj / dobj / res_pri / res_dual / gap agree to 1e-10 relative;
+  * default-settings solve (eps 1e-4): same status; delta-iterations REPORTED; gated |delta| <= 25 with Anderson
+    acceleration off (where the trajectory is reproducible up to CG stop decisions) and loosely (reported) with it
+    on -- AA amplifies 1e-16 differences (the reference's own LAPACK / no-LAPACK builds differ by thousands of
+    iterations); objective within 10 eps of the reference's and of the generator's optimum;
+  * the reference's universal checker verify_solution_correct (tests/verify.py, every clause) passes on our
+    solution.
+"""
+import ctypes as C
+import os
+import time
+
+import numpy as np
+import pytest
+
+from conftest import REF_DIR
+from scs_b200 import capi, problems
+import verify
+
+pytestmark = pytest.mark.gpu
+
+# (config, scale): n, m, nnz at these scales: C2 1e4/3e4/1e5, C3 2.5e3/2.5e3/2.5e4 (box + LP), C4 5e3/5.55e4/1e6 with
+# 10 PSD blocks of order 100, C5 1e4/3e4/1.5e5 (50 SOCs + PSD blocks of order 10)
+CASES = [("C2", 0.01), ("C3", 0.002), ("C4", 0.05), ("C5", 0.005)]
+# C3 (LP with a box cone) needs 2850 ADMM iterations = minutes of CPU time at ANY scale the reference can run
+# (65 000 at n=2500): its converged comparison is replaced by a fixed-window trajectory comparison below
+CONVERGED = [c for c in CASES if c[0] != "C3"]
+
+
+def solve(lib, prob, **over):
+    hp = capi.HostProblem(prob["A"], prob["b"], prob["c"], prob["cone"], prob.get("P"))
+    st = capi.default_settings(lib, verbose=0, **over)
+    x, y, s = np.zeros(hp.n), np.zeros(hp.m), np.zeros(hp.m)
+    sol = capi.ScsSolution(capi.dptr(x), capi.dptr(y), capi.dptr(s))
+    info = capi.ScsInfo()
+    status = lib.scs(C.byref(hp.data), C.byref(hp.cone), C.byref(st), C.byref(sol), C.byref(info))
+    return status, info, x, y, s, st
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+
+
+@pytest.mark.parametrize("cfg,scale", CASES)
+def test_config_one_iteration_1e10(lib, reflib, cfg, scale):
+    prob = problems.config(cfg, scale=scale)
+    st_m, im, x, y, s, _ = solve(lib, prob, max_iters=1)
+    st_r, ir, xr, yr, sr, _ = solve(reflib, prob, max_iters=1)
+    assert ir.lin_sys_solver.decode() == "sparse-indirect-scs"
+    assert st_m == st_r and im.iter == ir.iter == 1
+    errs = {nm: rel(a, b) for a, b, nm in ((x, xr, "x"), (y, yr, "y"), (s, sr, "s"))}
+    for fld in ("pobj", "dobj", "res_pri", "res_dual", "gap"):
+        a, b = getattr(im, fld), getattr(ir, fld)
+        errs[fld] = abs(a - b) / max(1.0, abs(b))
+    print(f"\n[{cfg} x{scale}] one-iteration parity vs reference: " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()))
+    for k, v in errs.items():
+        assert v <= 1e-10, (cfg, k, v)
+
+
+@pytest.mark.parametrize("cfg,scale", CONVERGED)
+@pytest.mark.parametrize("aa", [0, 10])
+def test_config_default_solve_matches_reference(lib, reflib, cfg, scale, aa):
+    prob = problems.config(cfg, scale=scale)
+    over = dict(acceleration_lookback=aa)
+    t0 = time.time()
+    st_m, im, x, y, s, stg = solve(lib, prob, **over)
+    t_m = time.time() - t0
+    t0 = time.time()
+    st_r, ir, xr, yr, sr, _ = solve(reflib, prob, **over)
+    t_r = time.time() - t0
+    eps = stg.eps_rel
+    d_it = im.iter - ir.iter
+    print(f"\n[{cfg} x{scale} aa={aa}] ours: {im.status.decode()} it={im.iter} pobj={im.pobj:.8e} "
+          f"res=({im.res_pri:.1e},{im.res_dual:.1e},{im.gap:.1e}) {t_m:.1f}s | reference: {ir.status.decode()} "
+          f"it={ir.iter} pobj={ir.pobj:.8e} res=({ir.res_pri:.1e},{ir.res_dual:.1e},{ir.gap:.1e}) {t_r:.1f}s | "
+          f"delta_iter={d_it:+d} rel dpobj={abs(im.pobj - ir.pobj) / max(1, abs(ir.pobj)):.1e}")
+    assert st_m == st_r == 1
+    assert abs(im.pobj - ir.pobj) <= 10 * eps * max(1.0, abs(ir.pobj))
+    assert abs(im.pobj - prob["opt"]) <= 10 * eps * max(1.0, abs(prob["opt"]))
+    if aa == 0:
+        # convergence is tested every 25 iterations (CONVERGED_INTERVAL): |delta| <= 25 means "same or adjacent check"
+        assert abs(d_it) <= 25, (cfg, im.iter, ir.iter)
+    else:
+        assert im.iter <= 2 * ir.iter + 100, (cfg, im.iter, ir.iter)
+    bad = verify.verify_solution_correct(prob, stg, im, x, y, s, st_m)
+    assert not bad, (cfg, bad)
+
+
+def test_c3_fixed_window_trajectory_matches_reference(lib, reflib):
+    """C3 (box + LP cone, the box Newton iteration with warm start across iterations): the first 100 ADMM iterations
+    without Anderson acceleration.  Iterations >= 2 solve the KKT system only to the adaptive CG tolerance, so the two
+    trajectories may differ by that tolerance (not by round-off): relative differences are REPORTED and gated at
+    1e-6; the reported residuals of both runs must agree to the same level."""
+    prob = problems.config("C3", scale=0.002)
+    over = dict(max_iters=100, acceleration_lookback=0)
+    st_m, im, x, y, s, _ = solve(lib, prob, **over)
+    st_r, ir, xr, yr, sr, _ = solve(reflib, prob, **over)
+    assert st_m == st_r == 2 and im.iter == ir.iter == 100      # solved (inaccurate - reached max_iters)
+    errs = {nm: rel(a, b) for a, b, nm in ((x, xr, "x"), (y, yr, "y"), (s, sr, "s"))}
+    for fld in ("pobj", "dobj", "res_pri", "res_dual", "gap"):
+        a, b = getattr(im, fld), getattr(ir, fld)
+        errs[fld] = abs(a - b) / max(1.0, abs(b))
+    print(f"\n[C3 x0.002, 100 iterations, AA off] vs reference: " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()))
+    for k, v in errs.items():
+        assert v <= 1e-6, (k, v)
+
+
+def test_full_size_c2_kkt_solve_vs_reference(lib):
+    """scs_solve_lin_sys at tol 1e-12 on the FULL C2 operator (n=1e6, m=3e6, nnz=1e7) against the reference's
+    CPU-indirect backend (OpenMP build for the SpMV, ~1 min of host time): <= 1e-10 relative."""
+    omp = os.path.join(REF_DIR, "libscsindir_ref_omp.so")
+    plain = os.path.join(REF_DIR, "libscsindir_ref.so")
+    path = omp if os.path.exists(omp) else plain
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built")
+    os.environ.setdefault("OMP_NUM_THREADS", str(min(32, os.cpu_count() or 1)))
+    ref = capi.load_reference(path)
+    rng = np.random.default_rng(1234)
+    n, m = 1_000_000, 3_000_000
+    A = problems.random_sparse_csc(m, n, 10, rng)
+    hp = capi.HostProblem(A, np.zeros(m), np.zeros(n), {"l": m})
+    z = 300_000
+    dr = np.empty(n + m + 1)
+    dr[:n], dr[n:n + z], dr[n + z:] = 1e-6, 1.0 / 100.0, 10.0
+    rhs = rng.standard_normal(n + m)
+    w = lib.scs_init_lin_sys_work(C.byref(hp.A), None, capi.dptr(dr))
+    assert w
+    a = rhs.copy()
+    t0 = time.time()
+    assert lib.scs_solve_lin_sys(w, capi.dptr(a), None, 1e-12) == 0
+    t_m = time.time() - t0
+    its = lib.scs_b200_linsys_last_cg_its(w)
+    lib.scs_free_lin_sys_work(w)
+    wr = ref.scs_init_lin_sys_work(C.byref(hp.A), None, capi.dptr(dr))
+    b = rhs.copy()
+    t0 = time.time()
+    assert ref.scs_solve_lin_sys(wr, capi.dptr(b), None, 1e-12) == 0
+    t_r = time.time() - t0
+    ref.scs_free_lin_sys_work(wr)
+    ex, ey = rel(a[:n], b[:n]), rel(a[n:], b[n:])
+    # the reduced residual recomputed on the host in fp64: || (R_x + A' R_y^-1 A) x - (r_x + A' R_y^-1 r_y) ||_inf
+    xs = a[:n]
+    t = problems.csc_matvec(A, xs) / dr[n:n + m]
+    lhs = dr[:n] * xs + problems.csc_rmatvec(A, t)
+    rr = rhs[:n] + problems.csc_rmatvec(A, rhs[n:] / dr[n:n + m])
+    res = float(np.abs(lhs - rr).max())
+    print(f"\n[C2 full KKT solve tol 1e-12] ours {its} CG iterations {t_m:.2f}s (incl. H2D/D2H) | reference {t_r:.1f}s | "
+          f"rel err x {ex:.2e} y {ey:.2e} | reduced residual (host fp64) {res:.2e}")
+    assert ex <= 1e-10 and ey <= 1e-10
+    assert res <= 1e-10
+
+
+def test_psd_c4_batch_200_blocks_of_order_100(lib, reflib):
+    """C4's cone: 200 PSD blocks of order 100 (+ LP rows) under the Moreau wrapper vs _scs_proj_dual_cone."""
+    cone = {"l": 1000, "s": [100] * 200}
+    m = capi.cone_rows(cone)
+    rng = np.random.default_rng(44)
+    x = rng.standard_normal(m) * 2.0
+    reflib._scs_init_cone.restype = C.c_void_p
+    reflib._scs_init_cone.argtypes = [C.POINTER(capi.ScsCone), C.c_int]
+    reflib._scs_proj_dual_cone.restype = C.c_int
+    reflib._scs_proj_dual_cone.argtypes = [capi.c_double_p, C.c_void_p, C.c_void_p, capi.c_double_p]
+    reflib._scs_finish_cone.argtypes = [C.c_void_p]
+    for ry in (None, np.full(m, 10.0)):
+        k, keep = capi.make_cone(cone)
+        cw = reflib._scs_init_cone(C.byref(k), m)
+        ref = x.copy()
+        t0 = time.time()
+        assert reflib._scs_proj_dual_cone(capi.dptr(ref), cw, None, capi.dptr(None if ry is None else ry.copy())) == 0
+        t_r = time.time() - t0
+        reflib._scs_finish_cone(cw)
+        k2, keep2 = capi.make_cone(cone)
+        mw = lib.scs_b200_init_cone(C.byref(k2), m, None)
+        assert mw
+        out = x.copy()
+        assert lib.scs_b200_proj_dual_cone(mw, capi.dptr(out), capi.dptr(None if ry is None else ry.copy())) == 0
+        t0 = time.time()
+        out = x.copy()
+        assert lib.scs_b200_proj_dual_cone(mw, capi.dptr(out), capi.dptr(None if ry is None else ry.copy())) == 0
+        t_m = time.time() - t0
+        lib.scs_b200_finish_cone(mw)
+        e = rel(out, ref)
+        print(f"\n[PSD 200 x k=100, metric={'on' if ry is not None else 'off'}] rel err {e:.2e}  ours {1e3 * t_m:.1f} ms "
+              f"(incl. H2D/D2H) reference {1e3 * t_r:.1f} ms")
+        assert e <= 5e-13

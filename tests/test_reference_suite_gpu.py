@@ -22,6 +22,12 @@ def test_reference_suite_through_b200_linsys_plugin():
     p = subprocess.run([exe], cwd=REF_DIR, env=env, capture_output=True, text=True, timeout=1200)
     tail = "\n".join(p.stdout.splitlines()[-15:])
     print(tail)
-    assert "sparse-indirect-b200" in p.stdout or True
+    # the binary must really be linked against OUR plugin: (i) the dynamic loader resolves libscs_b200_linsys.so,
+    # (ii) the solver header the reference prints (src/scs.c:127 "lin-sys:  %s") names our backend
+    ldd = subprocess.run(["ldd", exe], env=env, capture_output=True, text=True).stdout
+    assert "libscs_b200_linsys.so" in ldd, ldd
+    assert "libscsindir" not in ldd, ldd
+    assert "sparse-indirect-b200" in p.stdout, tail
+    assert "sparse-indirect-scs" not in p.stdout
     assert "ALL TESTS PASSED" in p.stdout, tail + p.stderr[-2000:]
     assert "Tests run: 57" in p.stdout

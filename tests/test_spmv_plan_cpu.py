@@ -213,7 +213,9 @@ def test_plan_and_lane_algorithm(lib, case):
     assert np.abs(y - ref).max() / scale <= 1e-14
 
 
-def test_long_rows_are_refused(lib):
+def test_long_rows_are_refused_when_the_split_is_switched_off(lib, monkeypatch):
+    """SCS_B200_SPMV_LONGROWS=0: an operator with a row longer than a warp-tile gets no v3 plan (-> v2 kernel)"""
+    monkeypatch.setenv("SCS_B200_SPMV_LONGROWS", "0")
     rng = np.random.default_rng(0)
     lens = np.array([3, MAXROW + 1, 2])
     rp, ci, va = random_csr(3, 500, rng, lens)
@@ -298,10 +300,10 @@ def test_plan_property_random_shapes(lib):
 
 
 def test_long_rows_as_virtual_rows(lib, monkeypatch):
-    """STAGED long-row mode (SCS_B200_SPMV_LONGROWS=1): rows longer than 124 entries are cut into balanced pieces
+    """long-row mode (the default): rows longer than 124 entries are cut into balanced pieces
     (an END flag per piece = one "virtual row"); the lane algorithm produces one sum per virtual row and the combine
     pass (spmv_combine_kernel) adds the pieces of each true row in order."""
-    monkeypatch.setenv("SCS_B200_SPMV_LONGROWS", "1")
+    monkeypatch.delenv("SCS_B200_SPMV_LONGROWS", raising=False)
     lib.b200_spmv3_plan_nvrows.restype = C.c_int
     lib.b200_spmv3_plan_nvrows.argtypes = [C.c_void_p]
     lib.b200_spmv3_plan_vptr.restype = C.POINTER(C.c_int)

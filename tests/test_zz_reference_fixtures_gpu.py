@@ -6,8 +6,9 @@ eps 1e-6, status solved, primal and dual objective within 1e-4 of the known opti
 random_prob exercises every supported cone at once (zero, LP, SOC incl. sizes 0 and 1, PSD incl. orders 0 and
 1, primal/dual exponential, primal/dual power); max_ent has 450 exponential cones; mpc_bug1..3 are QPs.
 
-NOT YET RUN ON HARDWARE: written after round 1's GPU budget was spent, hence the `gpu_unverified` marker
-(the file reader itself is verified on the CPU against the reference's reader in tests/test_rw_cpu.py)."""
+First green run on a B200: round 2, gpurun call A (profiles/r02a_first_call.log): 11 passed -- promoted from
+`gpu_unverified` to `gpu` (the file reader itself is verified on the CPU against the reference's reader in
+tests/test_rw_cpu.py)."""
 import ctypes as C
 import os
 
@@ -17,7 +18,7 @@ import pytest
 from conftest import REF_DIR
 from scs_b200 import capi
 
-pytestmark = pytest.mark.gpu_unverified
+pytestmark = pytest.mark.gpu
 PP = C.POINTER
 
 FIXTURES = {
@@ -31,8 +32,6 @@ FIXTURES = {
 
 @pytest.mark.parametrize("name", sorted(FIXTURES))
 def test_reference_fixture_known_optimum(lib, name):
-    if not lib.scs_b200_device_ok():
-        pytest.skip("no sm_100 device (this file is selected by -m 'not gpu' on CPU-only machines)")
     path = os.path.join(REF_DIR, "test", "problems", name)
     if not os.path.exists(path):
         pytest.skip("fixture not present (oracle/Makefile copies it where /root/reference exists)")
@@ -74,8 +73,6 @@ def test_reference_fixture_known_optimum(lib, name):
 def test_exp_power_operator_matches_committed_goldens(lib):
     """device exp / power cone kernels under the Moreau wrapper against tests/golden/cone_triples.npz
     (reference outputs); tolerances as in tests/test_cones_gpu.py (1e-8 max with power cones)."""
-    if not lib.scs_b200_device_ok():
-        pytest.skip("no sm_100 device")
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cone_triples.npz"))
     cone = {"l": 3, "ep": int(g["mixed_ep"]), "ed": int(g["mixed_ed"]), "p": list(g["mixed_p"])}
     m = capi.cone_rows(cone)
@@ -95,8 +92,6 @@ def test_exp_power_operator_matches_committed_goldens(lib):
 
 def test_complex_psd_operator_matches_reference(lib, reflib, monkeypatch):
     """staged complex-PSD kernels (kernels/cones_complex.cu, opt-in) against the reference's zheevr projection"""
-    if not lib.scs_b200_device_ok():
-        pytest.skip("no sm_100 device")
     monkeypatch.setenv("SCS_B200_COMPLEX_PSD", "1")
     reflib._scs_init_cone.restype = C.c_void_p
     reflib._scs_init_cone.argtypes = [PP(capi.ScsCone), C.c_int]
@@ -128,8 +123,6 @@ def test_full_size_configs_are_self_consistent(lib, cfg, steps):
     a fixed number of ADMM iterations, then the size-independent checks the reference applies to every solve
     (test/problem_utils.h:209-243): the reported residuals equal the ones recomputed on the host from (x, y, s) in
     fp64, s is in the cone and y in the dual cone, the duality gap is what the objectives say."""
-    if not lib.scs_b200_device_ok():
-        pytest.skip("no sm_100 device")
     from scs_b200 import problems
     prob = problems.config(cfg)
     hp = capi.HostProblem(prob["A"], prob["b"], prob["c"], prob["cone"])
@@ -156,11 +149,9 @@ def test_full_size_configs_are_self_consistent(lib, cfg, steps):
 
 
 def test_long_row_mode_matches_reference(lib, reflib, monkeypatch):
-    """STAGED v3 long-row mode (virtual rows + combine pass, SCS_B200_SPMV_LONGROWS=1): both operators and a KKT
+    """v3 long-row mode (virtual rows + combine pass, the default since round 2): both operators and a KKT
     solve on matrices with 700-entry columns and 40-entry rows / very long rows."""
-    if not lib.scs_b200_device_ok():
-        pytest.skip("no sm_100 device")
-    monkeypatch.setenv("SCS_B200_SPMV_LONGROWS", "1")
+    monkeypatch.delenv("SCS_B200_SPMV_LONGROWS", raising=False)
     from scs_b200 import problems
     reflib._scs_accum_by_a.argtypes = [PP(capi.ScsMatrix), capi.c_double_p, capi.c_double_p]
     reflib._scs_accum_by_atrans.argtypes = [PP(capi.ScsMatrix), capi.c_double_p, capi.c_double_p]

@@ -54,15 +54,28 @@ def main():
             return v * (1e9 if u.startswith("g") else 1e6 if u.startswith("m") else 1e3 if u.startswith("k") else 1.0)
 
         tr = {}
-        # launches alternate A x (even) / A'x (odd) in scripts/prof_spmv.py
-        for key, sel in (("A x", data[0::2]), ("A'x", data[1::2])):
+        # launches are classified by the kernel's template argument: spmv_flag_kernel<1> = K1 (POST_DIV, tmp = R_y^-1 A p),
+        # <2> = K2 (POST_FMA_DOT + alpha hook, Gp = R_x p + A' tmp) -- the in-loop kernels of scripts/prof_cg.py;
+        # <0> launches alternate A x (even) / A'x (odd) in scripts/prof_spmv.py
+        name = col["Kernel Name"]
+        groups = {"K1": [r for r in data if "spmv_flag_kernel<1>" in r[name]],
+                  "K2": [r for r in data if "spmv_flag_kernel<2>" in r[name]]}
+        plain = [r for r in data if "spmv_flag_kernel<0>" in r[name]]
+        groups["A x"], groups["A'x"] = plain[0::2], plain[1::2]
+        for key, sel in groups.items():
             if not sel:
                 continue
             tot = [to_bytes(num(r, "dram__bytes_read.sum"), units[col["dram__bytes_read.sum"]]) +
                    to_bytes(num(r, "dram__bytes_write.sum"), units[col["dram__bytes_write.sum"]]) for r in sel]
             tr[key] = {"dram_bytes_per_launch": sum(tot) / len(tot), "launches": len(tot),
-                       "kernel": sel[0][col["Kernel Name"]][:60], "source": os.path.basename(out)}
+                       "kernel": sel[0][name][:60], "source": os.path.basename(out)}
         p = os.path.join(os.path.dirname(out), "spmv_ncu_traffic.json")
+        try:
+            prev = json.load(open(p))
+        except Exception:
+            prev = {}
+        prev.update(tr)
+        tr = prev
         json.dump(tr, open(p, "w"), indent=1)
         print("wrote", p, tr)
 

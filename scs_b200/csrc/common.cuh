@@ -177,6 +177,34 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
       "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
+// ---------------------------------------------------------------- programmatic dependent launch (sm_90+)
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident while its
+// predecessor in the stream is still running: everything before pdl_wait() (barrier init, descriptor and matrix
+// prefetch -- data no predecessor writes) overlaps the predecessor's tail; pdl_wait() returns once the predecessor
+// grid has completed and its writes are visible. pdl_launch_dependents() lets the SUCCESSOR's CTAs be scheduled
+// as soon as every CTA of this grid has issued it (they then sit in their own pdl_wait()).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#ifdef __CUDACC__
+// host: launch `kernel` on `st`, optionally as a programmatic dependent of the previous kernel in the stream
+template <typename... KArgs, typename... Args>
+static inline cudaError_t b200_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                      bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg;
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

@@ -80,6 +80,8 @@ typedef struct {
   void *d_hook_arg;      /* B200CgCtl* for B200_HOOK_CG_ALPHA, B200P2pSignal* for B200_HOOK_P2P_SIGNAL */
   unsigned long long hook_val;
   const int *d_skip;     /* optional: kernel returns at once if *d_skip != 0 */
+  int pdl;               /* 1: launch as a programmatic dependent of the previous kernel in the stream (the kernel's
+                            prologue -- barrier init, first matrix stages -- overlaps that kernel's tail) */
 } B200SpmvArgs;
 
 int b200_spmv(const B200Spmv *M, const B200SpmvArgs *a);

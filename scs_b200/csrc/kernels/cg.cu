@@ -147,6 +147,8 @@ __global__ void __launch_bounds__(VEC_THREADS)
 k_cg_update(int n, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
             const double *__restrict__ Gp, const double *__restrict__ M, double *__restrict__ z,
             B200CgCtl *ctl, double *partials, unsigned int *counter) {
+  pdl_launch_dependents();  // K4's CTAs may become resident now; they wait for this grid in their own pdl_wait()
+  pdl_wait();               // K2 (Gp, alpha) complete and visible
   if (ctl->done) return;
   __shared__ double s_red[128];
   const double alpha = ctl->alpha;
@@ -208,6 +210,8 @@ k_cg_update(int n, double *__restrict__ x, double *__restrict__ r, const double 
 // K4 (private.c:212-214): p = z + beta p
 __global__ void __launch_bounds__(VEC_THREADS)
 k_cg_pupdate(int n, double *__restrict__ p, const double *__restrict__ z, const B200CgCtl *ctl) {
+  pdl_launch_dependents();  // the next iteration's K1 may start its prologue (barrier init, first matrix stages)
+  pdl_wait();               // K3 (z, beta, done) complete and visible
   if (ctl->done) return;
   const double beta = ctl->beta;
   const int n2 = n >> 1;
@@ -229,69 +233,6 @@ k_cg_pupdate(int n, double *__restrict__ p, const double *__restrict__ z, const 
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = fma(beta, p[n - 1], z[n - 1]);
 }
 
-
-// ---------------------------------------------------------------------------------------------
-// STAGED (not yet run on hardware; off unless SCS_B200_FUSE_K34=1): K3 and K4 in one cooperative launch.
-// K4 needs beta = z'r / z'r_prev, i.e. the grid-wide reduction of K3: the last block to finish K3 combines the
-// block partials in index order (same arithmetic as k_cg_update), updates the control block and releases a
-// generation flag; every block waits for it (one block per SM at most two, all co-resident) and then runs K4
-// on the elements it still has in L1 / L2. Saves one launch gap and the second pass's ramp-up per CG iteration.
-__global__ void __launch_bounds__(VEC_THREADS)
-k_cg_update_fused(int n, double *__restrict__ x, double *__restrict__ r, double *__restrict__ p,
-                  const double *__restrict__ Gp, const double *__restrict__ M, double *__restrict__ z,
-                  B200CgCtl *ctl, double *partials, unsigned int *counters, unsigned int gen) {
-  if (ctl->done) return;
-  __shared__ double s_red[128];
-  const double alpha = ctl->alpha, nalpha = -alpha;
-  const double ztr_old = ctl->ztr;
-  double acc0 = 0.0, acc1 = 0.0;
-  const int stride = gridDim.x * blockDim.x;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    double xv = x[i], rv = r[i], zv;
-    cg_update_elem(alpha, nalpha, xv, rv, p[i], Gp[i], M[i], zv, acc0, acc1);
-    x[i] = xv; r[i] = rv; z[i] = zv;
-  }
-  double sm[1] = {acc0}, mx[1] = {acc1};
-  block_sum<1>(sm, s_red);
-  block_max<1>(mx, s_red + 64);
-  if (threadIdx.x == 0) {
-    partials[blockIdx.x] = sm[0];
-    partials[2048 + blockIdx.x] = mx[0];
-    __threadfence();
-    if (atomicAdd(&counters[8], 1u) == gridDim.x - 1) {
-      counters[8] = 0u;
-      __threadfence();
-      double t0 = 0.0, t1 = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) {
-        t0 += __ldcg(&partials[b]);
-        t1 = fmax(t1, __ldcg(&partials[2048 + b]));
-      }
-      ctl->ztr_prev = ztr_old;
-      ctl->ztr = t0;
-      ctl->rnorm = t1;
-      ctl->iters += 1;
-      if (t1 < ctl->tol) {
-        ctl->done = 1;
-      } else if (ztr_old == 0.0) {
-        ctl->done = 1;
-      } else {
-        ctl->beta = t0 / ztr_old;
-        if (ctl->iters >= ctl->max_its) ctl->done = 1;
-      }
-      __threadfence();
-      *((volatile unsigned int *)&counters[9]) = gen;  // release
-    }
-    const long long t0c = clock64();
-    while (*((volatile unsigned int *)&counters[9]) != gen) {
-      if (clock64() - t0c > 20000000000LL) { ctl->pad[0] = 1; break; }
-    }
-    __threadfence();
-  }
-  __syncthreads();
-  if (*((volatile int *)&ctl->done)) return;
-  const double beta = *((volatile double *)&ctl->beta);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = fma(beta, p[i], z[i]);
-}
 
 __global__ void k_zero_if(long long len, double *__restrict__ v, const int *flag) {
   if (!*flag) return;
@@ -787,6 +728,16 @@ extern "C" int b200_cg_set_preconditioner(const B200Cg *cg, const double *d_Pdia
   return 0;
 }
 
+// programmatic dependent launch of the CG loop's kernels (SCS_B200_PDL=0 turns it off for A/B measurements)
+static int g_pdl = -1;
+static bool cg_pdl_enabled() {
+  if (g_pdl < 0) {
+    const char *e = getenv("SCS_B200_PDL");
+    g_pdl = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return g_pdl == 1;
+}
+
 // peer-memory reduction: 0 = automatic (one pass for 2 ranks, two-phase for more), 1 = one pass, 2 = two-phase
 static int g_p2p_mode = -1;
 extern "C" void scs_b200_set_p2p_mode(int mode) { g_p2p_mode = mode; }
@@ -856,7 +807,9 @@ static int mat_vec_sharded(B200Cg *cg, const double *d_x, double *d_y, int with_
 static int mat_vec(B200Cg *cg, const double *d_x, double *d_y, int with_dot, const int *d_skip) {
   if (cg->nranks > 1) return mat_vec_sharded(cg, d_x, d_y, with_dot, d_skip);
   B200SpmvArgs a;
+  memset(&a, 0, sizeof(a));
   // K1: tmp = (A x) ./ R_y
+  a.pdl = cg_pdl_enabled() ? 1 : 0;
   a.d_x = d_x; a.d_y = cg->d_tmp; a.d_init = nullptr; a.init_sign = 1.0;
   a.post = B200_POST_DIV; a.d_d = cg->d_ry; a.d_v = nullptr; a.d_dot = nullptr;
   a.hook = B200_HOOK_NONE; a.d_hook_arg = nullptr; a.d_skip = d_skip;
@@ -935,25 +888,12 @@ static int cg_iteration(B200Cg *cg, double *d_x) {
   if (g > 2 * b200_num_sms()) g = 2 * b200_num_sms();
   if (g < 1) g = 1;
   if (mat_vec(cg, cg->d_p, cg->d_Gp, 1, &cg->d_ctl->done) != 0) return -1;
-  {
-    static int fuse = -1;
-    static unsigned int gen = 0;
-    if (fuse < 0) {
-      const char *e = getenv("SCS_B200_FUSE_K34");
-      fuse = (e && atoi(e) != 0) ? 1 : 0;
-    }
-    if (fuse) {  // staged: K3 + K4 in one cooperative launch (all blocks co-resident: <= 2 per SM)
-      ++gen;
-      if (gen == 0) ++gen;
-      k_cg_update_fused<<<g, VEC_THREADS, 0, st>>>(n, d_x, cg->d_r, cg->d_p, cg->d_Gp, cg->d_M, cg->d_z, cg->d_ctl,
-                                                   cg->d_partials, cg->d_counter, gen);
-      b200_count_launch(1);
-      return 0;
-    }
-  }
-  k_cg_update<<<g, VEC_THREADS, 0, st>>>(n, d_x, cg->d_r, cg->d_p, cg->d_Gp, cg->d_M, cg->d_z,
-                                         cg->d_ctl, cg->d_partials, cg->d_counter);
-  k_cg_pupdate<<<g, VEC_THREADS, 0, st>>>(n, cg->d_p, cg->d_z, cg->d_ctl);
+  const bool pdl = cg_pdl_enabled();
+  CUDA_OK(b200_launch(k_cg_update, dim3(g), dim3(VEC_THREADS), 0, st, pdl, n, d_x, cg->d_r, (const double *)cg->d_p,
+                      (const double *)cg->d_Gp, (const double *)cg->d_M, cg->d_z, cg->d_ctl, cg->d_partials,
+                      cg->d_counter));
+  CUDA_OK(b200_launch(k_cg_pupdate, dim3(g), dim3(VEC_THREADS), 0, st, pdl, n, cg->d_p, (const double *)cg->d_z,
+                      (const B200CgCtl *)cg->d_ctl));
   b200_count_launch(2);
   return 0;
 }
@@ -1050,6 +990,7 @@ extern "C" int b200_cg_solve(B200Cg *cg, double *d_b, const double *d_s, double 
     b200_count_launch(1);
   } else {
     B200SpmvArgs a;
+    memset(&a, 0, sizeof(a));
     a.d_x = cg->d_tmp; a.d_y = d_b; a.d_init = d_b; a.init_sign = 1.0; a.post = B200_POST_NONE;
     a.d_d = nullptr; a.d_v = nullptr; a.d_dot = nullptr; a.hook = B200_HOOK_NONE;
     a.d_hook_arg = nullptr; a.d_skip = d_skip;
@@ -1108,6 +1049,7 @@ extern "C" int b200_cg_solve(B200Cg *cg, double *d_b, const double *d_s, double 
     if (b200_allgatherv(d_b + n, cg->offsets) != 0) return -1;
   } else {
     B200SpmvArgs a;
+    memset(&a, 0, sizeof(a));
     a.d_x = d_b; a.d_y = d_b + n; a.d_init = d_b + n; a.init_sign = -1.0; a.post = B200_POST_DIV;
     a.d_d = cg->d_ry; a.d_v = nullptr; a.d_dot = nullptr; a.hook = B200_HOOK_NONE;
     a.d_hook_arg = nullptr; a.d_skip = d_skip;

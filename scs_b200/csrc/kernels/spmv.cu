@@ -400,7 +400,9 @@ spmv_flag_kernel(const int *__restrict__ colidx, const double *__restrict__ vals
                  double init_sign, const double *__restrict__ d, const double *__restrict__ v,
                  double *dot_out, int hook, void *hook_arg, const int *skip, double *partials,
                  unsigned int *counter, unsigned long long hook_val) {
-  if (skip != nullptr && *((volatile const int *)skip) != 0) return;
+  // Programmatic dependent launch: nothing above pdl_wait() reads data a predecessor kernel writes -- the
+  // descriptors and the matrix stream are immutable -- so barrier init and the first ring stages overlap the
+  // predecessor's tail. `skip`, x, d, v, init are read only after the wait.
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *s_vals = reinterpret_cast<double *>(smem_raw);
   int *s_idx = reinterpret_cast<int *>(s_vals + SPMV3_STAGES * SPMV3_CAP);
@@ -422,8 +424,10 @@ spmv_flag_kernel(const int *__restrict__ colidx, const double *__restrict__ vals
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_launch_dependents();
 
   double dot_acc = 0.0;
+  int skipped = 0;
   if (wid == 0) {
     // ------------------------------------------------ producer (one elected lane)
     if (lane == 0) {
@@ -435,6 +439,7 @@ spmv_flag_kernel(const int *__restrict__ colidx, const double *__restrict__ vals
         const int4 l = __ldg(&g[SPMV3_NCW - 1]);
         ke_n = l.y + l.z;
       }
+      bool waited = false;
       for (int i = 0; i < nt; ++i) {
         const int st = i % SPMV3_STAGES, use = i / SPMV3_STAGES;
         const int ka = ka_n, cnt = (ke_n - ka_n + 3) & ~3;
@@ -443,23 +448,45 @@ spmv_flag_kernel(const int *__restrict__ colidx, const double *__restrict__ vals
           const int4 l = __ldg(&g[(size_t)(i + 2) * SPMV3_NCW - 1]);
           ke_n = l.y + l.z;
         }
-        if (use > 0) mbar_wait(&s_empty[st], (unsigned)((use - 1) & 1));
+        if (use > 0) {
+          if (!waited) {  // the first ring round was issued ahead of the predecessor's completion
+            pdl_wait();
+            waited = true;
+            if (skip != nullptr && *((volatile const int *)skip) != 0) { skipped = i; break; }
+          }
+          mbar_wait(&s_empty[st], (unsigned)((use - 1) & 1));
+        }
         mbar_expect_tx(&s_full[st], (unsigned)cnt * 12u + (unsigned)(SPMV3_NCW * 16));
         tma_load_1d(s_desc + (size_t)st * SPMV3_NCW, g + (size_t)i * SPMV3_NCW, SPMV3_NCW * 16,
                     &s_full[st], pol);
         tma_load_1d(s_idx + (size_t)st * SPMV3_CAP, colidx + ka, (unsigned)cnt * 4u, &s_full[st], pol);
         tma_load_1d(s_vals + (size_t)st * SPMV3_CAP, vals + ka, (unsigned)cnt * 8u, &s_full[st], pol);
       }
+      if (!waited) {
+        pdl_wait();
+        if (skip != nullptr && *((volatile const int *)skip) != 0) skipped = nt < SPMV3_STAGES ? nt : SPMV3_STAGES;
+      }
+      if (skipped) {
+        // the launch is a no-op (*skip set), but `skipped` stages are in flight into this CTA's shared memory:
+        // they must land before the CTA may exit
+        for (int i = 0; i < skipped && i < SPMV3_STAGES; ++i) mbar_wait(&s_full[i], 0u);
+      }
+    }
+    if (skip != nullptr) {  // the other lanes of the producer warp only need the decision for the tail below
+      if (lane != 0) pdl_wait();
+      skipped = (*((volatile const int *)skip) != 0) ? 1 : 0;
     }
   } else {
     // ------------------------------------------------ consumers: one warp-tile per warp per stage
+    pdl_wait();
+    if (skip != nullptr && *((volatile const int *)skip) != 0) skipped = 1;
     const int cw = wid - 1;
     double *ws = s_out + cw * SPMV3_WT;
     const unsigned FULL = 0xffffffffu;
     const unsigned lt = (1u << lane) - 1u;
     const unsigned le = lt | (1u << lane);
     const int sw = (lane >> 2) & 1;
-    for (int i = 0; i < nt; ++i) {
+    for (int i = 0; i < (skipped ? 0 : nt); ++i) {
       const int st = i % SPMV3_STAGES;
       const unsigned par = (unsigned)((i / SPMV3_STAGES) & 1);
       mbar_wait(&s_full[st], par);
@@ -583,6 +610,7 @@ spmv_flag_kernel(const int *__restrict__ colidx, const double *__restrict__ vals
     }
   }
 
+  if (skipped) return;  // uniform over the CTA: every thread read the same *skip after the predecessor completed
   if (hook == B200_HOOK_P2P_SIGNAL) {
     // multi-GPU: tell every peer that this rank's partial product is complete (last block only)
     __syncthreads();
@@ -1163,8 +1191,9 @@ extern "C" int b200_spmv(const B200Spmv *M, const B200SpmvArgs *a) {
 #define LAUNCH(POSTV)                                                                          \
   do {                                                                                         \
     if (M->version == 3)                                                                       \
-      spmv_flag_kernel<POSTV><<<grid, block, smem, st>>>(M->d_colidx, M->d_vals, M->d_wt3,     \
-                                                         M->d_cta_begin3, TAIL);               \
+      CUDA_OK(b200_launch(spmv_flag_kernel<POSTV>, grid, block, smem, st, a->pdl != 0,         \
+                          (const int *)M->d_colidx, (const double *)M->d_vals,                 \
+                          (const int4 *)M->d_wt3, (const int *)M->d_cta_begin3, TAIL));        \
     else spmv_ws_kernel<POSTV><<<grid, block, smem, st>>>(ARGS);                               \
   } while (0)
   if (M->version == 3 && M->d_vptr != nullptr) {

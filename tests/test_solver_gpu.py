@@ -52,15 +52,18 @@ def test_solver_matches_reference(lib, reflib, kind):
     st_r, info_r, xr, yr, sr = solve_with(reflib, prob, eps_abs=eps, eps_rel=eps, max_iters=30000)
     assert info_r.lin_sys_solver.decode() == "sparse-indirect-scs"   # really the reference
     print(f"\n[{kind}] mine: {info_m.status.decode()} it={info_m.iter} pobj={info_m.pobj:.12e} "
-          f"res_pri={info_m.res_pri:.2e} | ref: {info_r.status.decode()} it={info_r.iter} pobj={info_r.pobj:.12e}")
+          f"res_pri={info_m.res_pri:.2e} | ref: {info_r.status.decode()} it={info_r.iter} pobj={info_r.pobj:.12e} | "
+          f"delta_iter={info_m.iter - info_r.iter:+d}")
     assert st_m == st_r == 1
     assert info_m.lin_sys_solver.decode().startswith("sparse-indirect-b200")
     # converged quantities agree (trajectories are not reproducible even between two CPU
     # builds of the reference -- SURVEY.md section 7 -- so iteration counts may differ)
     assert abs(info_m.pobj - info_r.pobj) <= 100 * eps * max(1.0, abs(info_r.pobj))
     assert abs(info_m.pobj - prob["opt"]) <= 1000 * eps * max(1.0, abs(prob["opt"]))
-    # iteration counts / minimisers are not reproducible (AA amplifies rounding; degenerate LPs),
-    # see test_one_iteration_matches_reference for the sharp end-to-end check
+    # iteration counts / minimisers are not reproducible WITH Anderson acceleration at eps 1e-9 (AA amplifies
+    # rounding; degenerate LPs; the reference's own two builds differ by >10x here): delta_iter
+    # is REPORTED above and bounded loosely; the |delta| <= 25 gate of SURVEY 8(d) is applied where the trajectory is
+    # reproducible -- AA off, default eps -- in tests/test_parity_configs_gpu.py
     assert info_m.iter <= 4 * info_r.iter + 100
     # the reference's own universal checker, recomputed here (test/problem_utils.h:107-249)
     A = prob["A"]
@@ -76,18 +79,21 @@ def test_solver_matches_reference(lib, reflib, kind):
 @pytest.mark.parametrize("kind", ["lp", "socp", "box", "sdp", "mixed"])
 def test_one_iteration_matches_reference(lib, reflib, kind):
     """max_iters=1: equilibration + KKT solve at tol 1e-12 + cone projection + un-normalisation,
-    end to end through scs(); agreement to 1e-9 relative on x, y, s."""
+    end to end through scs(); agreement to 1e-10 relative on x, y, s and the ScsInfo residuals (north star)."""
     prob = small_problem(kind, seed=11)
     st_m, info_m, x, y, s = solve_with(lib, prob, max_iters=1)
     st_r, info_r, xr, yr, sr = solve_with(reflib, prob, max_iters=1)
     assert info_r.lin_sys_solver.decode() == "sparse-indirect-scs"
     assert st_m == st_r and info_m.iter == info_r.iter == 1
+    errs = {}
     for a, b, nm in ((x, xr, "x"), (y, yr, "y"), (s, sr, "s")):
-        err = np.abs(a - b).max() / max(1.0, np.abs(b).max())
-        assert err <= 1e-9, (kind, nm, err)
+        errs[nm] = np.abs(a - b).max() / max(1.0, np.abs(b).max())
     for fld in ("pobj", "dobj", "res_pri", "res_dual", "gap"):
         a, b = getattr(info_m, fld), getattr(info_r, fld)
-        assert abs(a - b) <= 1e-9 * max(1.0, abs(b)), (kind, fld, a, b)
+        errs[fld] = abs(a - b) / max(1.0, abs(b))
+    print(f"\n[{kind}] one-iteration parity: " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()))
+    for k, v in errs.items():
+        assert v <= 1e-10, (kind, k, v)
 
 
 def qp_problem(seed):
@@ -116,10 +122,10 @@ def test_qp_matches_reference(lib, reflib):
     assert st_m == st_r and info_m.iter == info_r.iter == 1
     for a, b, nm in ((x, xr, "x"), (y, yr, "y"), (s, sr, "s")):
         err = np.abs(a - b).max() / max(1.0, np.abs(b).max())
-        assert err <= 1e-9, (nm, err)
+        assert err <= 1e-10, (nm, err)
     for fld in ("pobj", "dobj", "res_pri", "res_dual", "gap"):
         a, b = getattr(info_m, fld), getattr(info_r, fld)
-        assert abs(a - b) <= 1e-9 * max(1.0, abs(b)), (fld, a, b)
+        assert abs(a - b) <= 1e-10 * max(1.0, abs(b)), (fld, a, b)
     eps = 1e-7
     st_m, info_m, x, y, s = solve_with(lib, prob, eps_abs=eps, eps_rel=eps, max_iters=30000)
     st_r, info_r, xr, yr, sr = solve_with(reflib, prob, eps_abs=eps, eps_rel=eps, max_iters=30000)

@@ -88,8 +88,7 @@ B200Cones *b200_cones_create(int m, int nz, int nl, int bsize, const double *h_b
 int b200_cones_set_triples(B200Cones *c, int ep, int ed, int psize, const double *h_p);
 int b200_cone_triples_project(int n_exp_primal, int n_exp_dual, int n_pow, long long exp_off,
                               const double *d_pow, double *d_x, const double *d_s, const double *d_ry);
-/* complex PSD blocks (kernels/cones_complex.cu, STAGED: not yet run on hardware; the host side enables them
- * only with SCS_B200_COMPLEX_PSD=1). n_triples = ep + ed + psize. */
+/* complex PSD blocks (kernels/cones_complex.cu; reference cones.c:1072-1156). n_triples = ep + ed + psize. */
 typedef struct B200CpsdCones B200CpsdCones;
 B200CpsdCones *b200_cpsd_create(int cssize, const int *h_cs, long long first_row);
 int b200_cpsd_project(B200CpsdCones *c, double *d_x, const double *d_s, const double *d_ry);

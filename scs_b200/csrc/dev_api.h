@@ -59,13 +59,25 @@ const int *b200_spmv_rowptr(const B200Spmv *M);    /* device */
 double b200_spmv_alg_bytes(const B200Spmv *M, int extra_row_vectors);
 
 enum { B200_POST_NONE = 0, B200_POST_DIV = 1, B200_POST_FMA_DOT = 2, B200_POST_FMA = 3 };
-enum { B200_HOOK_NONE = 0, B200_HOOK_CG_ALPHA = 1, B200_HOOK_P2P_SIGNAL = 2 };
+enum { B200_HOOK_NONE = 0, B200_HOOK_CG_ALPHA = 1, B200_HOOK_P2P_SIGNAL = 2, B200_HOOK_P2P_ROUTE = 3 };
 /* B200_HOOK_P2P_SIGNAL: when the LAST block of the launch has stored its rows, it publishes
  * hook_val into slot `rank` of every peer's flag line (d_hook_arg -> B200P2pSignal). */
 typedef struct {
   int nranks, rank;
   unsigned long long *flags[8]; /* flags[r]: flag line of rank r as mapped in this process */
 } B200P2pSignal;
+
+/* B200_HOOK_P2P_ROUTE (POST_NONE only, flagged-stream kernel): output row j is not stored to d_y but PUSHED over
+ * NVLink into the inbox of the rank that owns slice [lo[o], lo[o+1]) of the output space: dst[o][j - lo[o]]
+ * (dst[o] = this rank's lane of rank o's inbox as mapped in this process; lo[nranks] = nrows). When the last
+ * block has stored its rows it publishes hook_val into slot `rank` of every peer's flag line, like
+ * B200_HOOK_P2P_SIGNAL. The SpMV thereby IS the reduce-scatter send of the sharded-x CG (kernels/cg.cu). */
+typedef struct {
+  int nranks, rank;
+  int lo[9];
+  double *dst[8];
+  unsigned long long *flags[8];
+} B200P2pRoute;
 
 typedef struct {
   const double *d_x;     /* gather vector, length ncols */
@@ -77,7 +89,7 @@ typedef struct {
   const double *d_v;
   double *d_dot;         /* B200_POST_FMA_DOT: receives sum_r v[r]*y[r] */
   int hook;              /* B200_HOOK_*: run by the last block after the dot is final */
-  void *d_hook_arg;      /* B200CgCtl* for B200_HOOK_CG_ALPHA, B200P2pSignal* for B200_HOOK_P2P_SIGNAL */
+  void *d_hook_arg;      /* B200CgCtl* for B200_HOOK_CG_ALPHA, B200P2pSignal* / B200P2pRoute* for the P2P hooks */
   unsigned long long hook_val;
   const int *d_skip;     /* optional: kernel returns at once if *d_skip != 0 */
   int pdl;               /* 1: launch as a programmatic dependent of the previous kernel in the stream (the kernel's
@@ -85,6 +97,7 @@ typedef struct {
 } B200SpmvArgs;
 
 int b200_spmv(const B200Spmv *M, const B200SpmvArgs *a);
+int b200_spmv_can_route(const B200Spmv *M); /* 1: B200_HOOK_P2P_ROUTE is available for this operator */
 /* per-launch CUDA-event timing of M0 and M1 launched alternately (cold L2), ms per launch */
 int b200_spmv_time_pair(const B200Spmv *M0, const B200Spmv *M1, int reps, double *out_ms);
 
@@ -120,6 +133,8 @@ typedef struct {
   double *d_red;       /* n: partial A_g' z before the all-reduce */
   int use_p2p;         /* 1: fused peer-memory reduction instead of the NCCL all-reduce */
   B200P2pSignal *d_p2p_sig; /* device copy of the peer flag table */
+  B200P2pRoute *d_p2p_route; /* device copy of the push-routing table (sharded-x mode); d_p then lives in the
+                                peer-mapped exchange allocation */
 } B200Cg;
 
 /* M_j = 1 / (R_x,j + P_jj + sum_k A_kj^2 / R_y,k)   (private.c:50-82) */
@@ -146,6 +161,10 @@ int b200_p2p_ok(int n);
 int b200_p2p_stride(void);
 double *b200_p2p_base(int r);
 unsigned long long *b200_p2p_flags(int r);
+double *b200_p2p_pvec(int r);   /* rank r's p vector inside its exchange allocation (sharded-x mode) */
+double *b200_p2p_inbox(int r);  /* rank r's inbox [G][ceil(n/G)] */
+int b200_p2p_claim_pvec(void);  /* the exchange p vector serves one workspace at a time; 0 = claimed */
+void b200_p2p_release_pvec(void);
 unsigned long long b200_p2p_next_seq(void);
 
 /* ------------------------------------------------------------ vector ops - */

@@ -306,7 +306,7 @@ ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
   w->d_b = (double *)b200_malloc(((size_t)n + m) * 8);
   w->d_s = (double *)b200_malloc((size_t)n * 8);
   w->cg.d_M = (double *)b200_malloc((size_t)n * 8);
-  w->cg.d_p = (double *)b200_malloc((size_t)n * 8);
+  w->cg.d_p = SCS_NULL; /* allocated below: in the peer-mapped exchange memory when the sharded-x mode is possible */
   w->cg.d_r = (double *)b200_malloc((size_t)n * 8);
   w->cg.d_Gp = (double *)b200_malloc((size_t)n * 8);
   w->cg.d_z = (double *)b200_malloc((size_t)n * 8);
@@ -316,7 +316,7 @@ ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
   w->cg.d_counter = (unsigned int *)b200_malloc(64);
   w->cg.d_red = (double *)b200_malloc((size_t)n * 8);
   w->cg.h_ctl = (B200CgCtl *)b200_host_alloc(sizeof(B200CgCtl));
-  if (!w->d_diag_r || !w->d_b || !w->d_s || !w->cg.d_M || !w->cg.d_p || !w->cg.d_r ||
+  if (!w->d_diag_r || !w->d_b || !w->d_s || !w->cg.d_M || !w->cg.d_r ||
       !w->cg.d_Gp || !w->cg.d_z || !w->cg.d_tmp || !w->cg.d_ctl || !w->cg.d_partials ||
       !w->cg.d_counter || !w->cg.h_ctl || !w->cg.d_red)
     goto fail;
@@ -338,6 +338,28 @@ ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
     for (r = 0; r < w->nranks && r < 8; ++r) sig.flags[r] = b200_p2p_flags(r);
     w->cg.d_p2p_sig = (B200P2pSignal *)b200_malloc(sizeof(sig));
     if (!w->cg.d_p2p_sig || b200_h2d(w->cg.d_p2p_sig, &sig, sizeof(sig)) != 0) goto fail;
+    /* sharded-x push mode (kernels/cg.cu k_cgx_iteration): p lives in the exchange allocation so that the peers can
+     * store their slices into it, and the K2 SpMV pushes its rows to the owners' inboxes. Needs the flagged-stream
+     * kernel without virtual rows for A' and the (single) exchange p vector. */
+    if (b200_spmv_can_route(w->At) && b200_p2p_claim_pvec() == 0) {
+      B200P2pRoute rt;
+      const int G = w->nranks, S = (n + G - 1) / G;
+      memset(&rt, 0, sizeof(rt));
+      rt.nranks = G; rt.rank = w->rank;
+      for (r = 0; r <= G; ++r) rt.lo[r] = (int)(((long long)n * r) / G);
+      for (r = 0; r < G; ++r) {
+        rt.dst[r] = b200_p2p_inbox(r) + (size_t)w->rank * S; /* my lane of rank r's inbox */
+        rt.flags[r] = b200_p2p_flags(r);
+      }
+      w->p_in_exchange = 1;
+      w->cg.d_p = b200_p2p_pvec(w->rank);
+      w->cg.d_p2p_route = (B200P2pRoute *)b200_malloc(sizeof(rt));
+      if (!w->cg.d_p2p_route || b200_h2d(w->cg.d_p2p_route, &rt, sizeof(rt)) != 0) goto fail;
+    }
+  }
+  if (!w->cg.d_p) {
+    w->cg.d_p = (double *)b200_malloc((size_t)n * 8);
+    if (!w->cg.d_p) goto fail;
   }
   if (b200_h2d(w->d_diag_r, diag_r, ((size_t)n + m) * 8) != 0) goto fail;
   if (b200_cg_set_preconditioner(&w->cg, w->d_Pdiag) != 0) goto fail;
@@ -360,7 +382,7 @@ void scs_free_lin_sys_work(ScsLinSysWork *w) {
   b200_free(w->d_b);
   b200_free(w->d_s);
   b200_free(w->cg.d_M);
-  b200_free(w->cg.d_p);
+  if (w->p_in_exchange) b200_p2p_release_pvec(); else b200_free(w->cg.d_p);
   b200_free(w->cg.d_r);
   b200_free(w->cg.d_Gp);
   b200_free(w->cg.d_z);
@@ -370,6 +392,7 @@ void scs_free_lin_sys_work(ScsLinSysWork *w) {
   b200_free(w->cg.d_counter);
   b200_free(w->cg.d_red);
   b200_free(w->cg.d_p2p_sig);
+  b200_free(w->cg.d_p2p_route);
   b200_host_free(w->cg.h_ctl);
   free(w->offsets);
   free(w);

@@ -20,6 +20,7 @@ struct SCS_LIN_SYS_WORK {
   B200Cg cg;
   /* row-sharded mode: this rank owns rows [row0, row0+mloc); offsets has nranks+1 entries */
   int nranks, rank, row0, mloc;
+  int p_in_exchange; /* cg.d_p points into the peer-mapped exchange allocation (sharded-x mode): not ours to free */
   int *offsets;
   int last_cg_its;
   long long tot_cg_its;

@@ -21,10 +21,6 @@ ScsB200ConeWork *scs_b200_init_cone(const ScsCone *k, scs_int m, const scs_float
   int j;
   long long dims;
   if (!k || m <= 0) return SCS_NULL;
-  if (k->cssize > 0 && !getenv("SCS_B200_COMPLEX_PSD")) {
-    fprintf(stderr, "scs_b200: the complex-PSD cone is staged, not enabled (set SCS_B200_COMPLEX_PSD=1)\n");
-    return SCS_NULL;
-  }
   if (k->cssize < 0 || (k->cssize > 0 && !k->cs)) return SCS_NULL;
   if (k->ep < 0 || k->ed < 0 || k->psize < 0 || (k->psize > 0 && !k->p)) return SCS_NULL;
   dims = (long long)k->z + k->l + k->bsize;

@@ -134,13 +134,6 @@ static int validate_cones(const ScsData *d, const ScsCone *k) {
     printf("cone dimension error\n");
     return -1;
   }
-  if (k->cssize > 0 && !getenv("SCS_B200_COMPLEX_PSD")) {
-    /* scope: zero / LP / box / SOC / PSD + exp / power (8f-3). No CPU fallback. The complex
-     * PSD kernels (kernels/cones_complex.cu) are staged and not yet run on hardware: opt in explicitly. */
-    printf("ERROR: scs_b200 does not enable the complex-PSD cone by default (zero, linear, box, second-order, PSD, "
-           "exponential and power cones are supported; SCS_B200_COMPLEX_PSD=1 enables the staged kernels)\n");
-    return -1;
-  }
   if (k->cssize > 0) {
     if (!k->cs) { printf("complex sd cone array missing\n"); return -1; }
     for (i = 0; i < k->cssize; ++i)

@@ -475,27 +475,34 @@ k_cg_finish_p2p2(int n, double *__restrict__ y, P2pView pv, unsigned long long s
 
 
 // ---------------------------------------------------------------------------------------------
-// STAGED (written after round 1's GPU budget was spent; NOT yet run on hardware; off unless
-// SCS_B200_SHARD_X=1 / scs_b200_set_shard_x(1)): "sharded-x" CG iteration for G >= 2 ranks.
-// p stays replicated (it is the SpMV gather vector); x, r, z and Gp are owned by n-slices
-// [n g/G, n (g+1)/G). After K1 / K2 (the rank's partial A_g' R_g^-1 A_g p sits in its exchange buffer and
-// "partial ready" is signalled) ONE cooperative kernel per rank does the rest of the iteration:
-//   1  wait for all partials; reduce MY slice in rank order (remote loads), Gp = R_x p (+ P p) + sum,
-//      block-reduce p'Gp over the slice; the last block publishes the slice's p'Gp to every rank;
-//   2  wait for the G partial scalars, add them in rank order => p'Gp and alpha, identical bits everywhere;
-//   3  K3 on the slice (x, r, z; z'r and ||r||_inf partials), published the same way;
-//   4  wait, combine => z'r, ||r||_inf, the stop decision and beta, identical everywhere;
-//   5  K4 on the slice: p = z + beta p, written to the local p and to the rank's p-exchange buffer; the last
-//      block records the iteration in the control block and publishes "p slice ready";
-//   6  wait, copy the other ranks' p slices into the local p.
-// Remote volume 2 (G-1)/G n doubles as in the two-phase reduction, but K3 / K4 shrink by G and no rank
-// touches a full n-vector except p. All blocks spin on flags, so the grid must be co-resident (<= #SMs).
-// Exchange memory: the rank's partial buffer red[2][n], its p-exchange buffer (the rs[2][n] area of the
-// two-phase mode), flag slots 0..7 "partial", 16..23 / 24..31 "scalars of round 1 / 2", 32..39 "p slice",
-// and 64 doubles of scalar slots after the flag line: [round][parity][rank][2].
+// "Sharded-x" CG iteration for G >= 2 ranks, PUSH-based (SCS_B200_SHARD_X=1 / scs_b200_set_shard_x(1)).
+// p stays replicated (it is the SpMV gather vector) but lives in the peer-mapped exchange allocation; x, r, z and
+// Gp are owned by n-slices [n g/G, n (g+1)/G). Data only ever moves by STORES into peer memory (NVLink writes
+// pipeline; remote loads pay the full round trip), synchronisation is by sequence-numbered flags:
+//   K1  tmp_g = R_g^-1 A_g p                                   local SpMV
+//   K2  partial_g = A_g' tmp_g, every output row pushed into the inbox of the rank that owns it by the SpMV
+//       epilogue itself (B200_HOOK_P2P_ROUTE = the reduce-scatter send); its last block publishes "partial ready"
+//   K34 ONE kernel per rank (this one):
+//       1  wait for the G-1 peer partials; sum MY slice from the LOCAL inbox in rank order, Gp = R_x p (+ P p) + sum,
+//          block-reduce p'Gp over the slice; the last block pushes the slice's p'Gp to every rank;
+//       2  wait for the G partial scalars, add them in rank order => p'Gp and alpha, identical bits everywhere;
+//       3  K3 on the slice (x, r, z; z'r and ||r||_inf partials), pushed the same way;
+//       4  wait, combine => z'r, ||r||_inf, the stop decision and beta, identical everywhere;
+//       5  K4 on the slice: p = z + beta p, stored into EVERY rank's p (the all-gather is G-1 remote stores per
+//          element); the last block records the iteration in the control block and publishes "p slice ready";
+//       6  wait for the peers' p slices (the next K1 gathers from all of p).
+// No buffer needs double-buffering: a rank can enter iteration k+1 only after every peer has published its p slice
+// of iteration k, i.e. after every peer has finished reading its inbox and scalar slots of iteration k
+// (tests/test_shardx_protocol_cpu.py emulates the protocol with threads and random delays).
+// Remote volume per rank and iteration: 2 (G-1)/G n doubles OUT; K3 / K4 shrink by G. All blocks spin on flags, so
+// the grid must be co-resident (<= #SMs blocks).
+// Exchange allocation (comm.cu): [0, 4n) buffers of the replicated modes, [4n, 5n) p, [5n, 6n+16) inbox
+// [G][S] with S = ceil(n / G), then the flag line (slots 0..7 "partial", 16..23 / 24..31 "scalars of round 1 / 2",
+// 32..39 "p slice") and 64 doubles of scalar slots [round][parity][rank][2].
 struct P2pViewX {
-  int nranks, rank, stride;
-  const double *base[8];
+  int nranks, rank, S;
+  const double *inbox;          // local: inbox[q * S + (i - lo)] = rank q's partial for my element i
+  double *peer_p[8];            // peer_p[q]: rank q's p vector as mapped here (peer_p[rank] == local p)
   unsigned long long *flags[8];
 };
 __device__ __forceinline__ double *px_scal(const P2pViewX &pv, int r, int round, int parity, int from) {
@@ -514,8 +521,8 @@ __device__ __forceinline__ void px_wait(volatile unsigned long long *line, int f
 }
 
 __global__ void __launch_bounds__(VEC_THREADS)
-k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int do_signal, int y_has_px,
-                const double *__restrict__ rx, const double *__restrict__ M, double *__restrict__ p,
+k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int y_has_px,
+                const double *__restrict__ rx, const double *__restrict__ M, double *p,
                 double *__restrict__ Gp, double *__restrict__ x, double *__restrict__ r,
                 double *__restrict__ z, B200CgCtl *ctl, double *partials, unsigned int *counters) {
   if (ctl->done) return;
@@ -523,8 +530,6 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int do_signal, int y
   __shared__ double s_bc[4];
   const int G = pv.nranks, me = pv.rank;
   const int parity = (int)(seq & 1ull);
-  const size_t slot = (size_t)parity * pv.stride;
-  const size_t pex = (size_t)2 * pv.stride + slot;
   const long long lo = (long long)n * me / G, hi = (long long)n * (me + 1) / G;
   const long long gstride = (long long)gridDim.x * blockDim.x;
   const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -533,20 +538,13 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int do_signal, int y
   const double ztr_old = ctl->ztr, tol = ctl->tol;
   const int iters_old = ctl->iters, max_its = ctl->max_its;
 
-  // ---- 1: partials ready -> my slice of G p, partial p'Gp
-  if (threadIdx.x == 0) {
-    if (do_signal && blockIdx.x == 0) {
-      __threadfence_system();
-      for (int q = 0; q < G; ++q)
-        if (q != me) *((volatile unsigned long long *)(pv.flags[q] + me)) = seq;
-    }
-    px_wait(myflags, 0, G, me, seq, ctl);
-  }
+  // ---- 1: peer partials have landed in my inbox -> my slice of G p, partial p'Gp
+  if (threadIdx.x == 0) px_wait(myflags, 0, G, me, seq, ctl);
   __syncthreads();
   double acc = 0.0;
   for (long long i = lo + gtid; i < hi; i += gstride) {
     double sum = 0.0;
-    for (int q = 0; q < G; ++q) sum += __ldcg(pv.base[q] + slot + i);  // rank order
+    for (int q = 0; q < G; ++q) sum += __ldcg(pv.inbox + (size_t)q * pv.S + (i - lo));  // rank order
     const double base = y_has_px ? Gp[i] + sum : sum;
     const double pi = p[i];
     const double out = fma(rx[i], pi, base);
@@ -642,13 +640,11 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int do_signal, int y
   const double ztr_new = s_bc[0], rnorm = s_bc[1], beta = s_bc[2];
   const int done = s_bc[3] != 0.0;
 
-  // ---- 5: K4 on the slice (skipped once the stop test fired, like k_cg_pupdate)
+  // ---- 5: K4 on the slice, pushed into every rank's p (skipped once the stop test fired, like k_cg_pupdate)
   if (!done) {
-    double *mine = const_cast<double *>(pv.base[me]) + pex;
     for (long long i = lo + gtid; i < hi; i += gstride) {
       const double pn = fma(beta, p[i], z[i]);
-      p[i] = pn;
-      mine[i] = pn;
+      for (int q = 0; q < G; ++q) pv.peer_p[q][i] = pn;  // q == me: the local p
     }
   }
   __syncthreads();
@@ -667,17 +663,10 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int do_signal, int y
       __threadfence_system();
       for (int q = 0; q < G; ++q) *((volatile unsigned long long *)(pv.flags[q] + 32 + me)) = seq;
     }
-    // ---- 6: the other slices of the new p
-    if (!done) px_wait(myflags, 32, G, -1, seq, ctl);
+    // ---- 6: the peers' slices of the new p have landed in my p
+    if (!done) px_wait(myflags, 32, G, me, seq, ctl);
   }
   __syncthreads();
-  if (done) return;
-  for (int q = 0; q < G; ++q) {
-    if (q == me) continue;
-    const long long qlo = (long long)n * q / G, qhi = (long long)n * (q + 1) / G;
-    const double *src = pv.base[q] + pex;
-    for (long long i = qlo + gtid; i < qhi; i += gstride) p[i] = __ldcg(src + i);
-  }
 }
 
 __global__ void k_add_if_not(int n, double *__restrict__ a, const double *__restrict__ b, const int *skip) {
@@ -831,7 +820,7 @@ static int mat_vec(B200Cg *cg, const double *d_x, double *d_y, int with_dot, con
   return b200_spmv(cg->At, &a);
 }
 
-// staged sharded-x mode (see k_cgx_iteration): -1 = read SCS_B200_SHARD_X once, 0 = off (default), 1 = on
+// sharded-x push mode (see k_cgx_iteration): -1 = read SCS_B200_SHARD_X once, 0 = off, 1 = on
 static int g_shard_x = -1;
 extern "C" void scs_b200_set_shard_x(int on) { g_shard_x = on ? 1 : 0; }
 static int shard_x_active(const B200Cg *cg) {
@@ -839,7 +828,7 @@ static int shard_x_active(const B200Cg *cg) {
     const char *e = getenv("SCS_B200_SHARD_X");
     g_shard_x = (e && atoi(e) != 0) ? 1 : 0;
   }
-  return g_shard_x == 1 && cg->nranks > 1 && cg->use_p2p && cg->d_p2p_sig != nullptr;
+  return g_shard_x == 1 && cg->nranks > 1 && cg->use_p2p && cg->d_p2p_route != nullptr;
 }
 
 static int cg_iteration_shard_x(B200Cg *cg, double *d_x) {
@@ -851,29 +840,31 @@ static int cg_iteration_shard_x(B200Cg *cg, double *d_x) {
   a.d_x = cg->d_p; a.d_y = cg->d_tmp + cg->row0; a.init_sign = 1.0; a.post = B200_POST_DIV;
   a.d_d = cg->d_ry + cg->row0; a.d_skip = d_skip;
   if (b200_spmv(cg->A, &a) != 0) return -1;
-  // K2: partial A_g' tmp_g into this rank's exchange buffer; its last block signals "partial ready"
+  // K2: partial A_g' tmp_g, every row pushed to its owner's inbox; the last block signals "partial ready"
   const unsigned long long seq = b200_p2p_next_seq();
   a.d_x = cg->d_tmp + cg->row0;
-  a.d_y = b200_p2p_base(b200_comm_rank()) + (size_t)(seq & 1ull) * b200_p2p_stride();
+  a.d_y = cg->d_red;  // not written in routed mode
   a.post = B200_POST_NONE; a.d_d = nullptr;
-  a.hook = B200_HOOK_P2P_SIGNAL; a.d_hook_arg = cg->d_p2p_sig; a.hook_val = seq;
+  a.hook = B200_HOOK_P2P_ROUTE; a.d_hook_arg = cg->d_p2p_route; a.hook_val = seq;
   if (b200_spmv(cg->At, &a) != 0) return -1;
   if (cg->P) {  // P is replicated: Gp = P p on every rank, the slice kernel adds the rest
     memset(&a, 0, sizeof(a));
     a.d_x = cg->d_p; a.d_y = cg->d_Gp; a.init_sign = 1.0; a.post = B200_POST_NONE; a.d_skip = d_skip;
     if (b200_spmv(cg->P, &a) != 0) return -1;
   }
+  const int G = cg->nranks, me = b200_comm_rank();
   P2pViewX pv;
-  pv.nranks = cg->nranks; pv.rank = b200_comm_rank(); pv.stride = b200_p2p_stride();
+  pv.nranks = G; pv.rank = me; pv.S = (cg->n + G - 1) / G;
+  pv.inbox = b200_p2p_inbox(me);
   for (int r = 0; r < 8; ++r) {
-    pv.base[r] = r < cg->nranks ? b200_p2p_base(r) : nullptr;
-    pv.flags[r] = r < cg->nranks ? b200_p2p_flags(r) : nullptr;
+    pv.peer_p[r] = r < G ? b200_p2p_pvec(r) : nullptr;
+    pv.flags[r] = r < G ? b200_p2p_flags(r) : nullptr;
   }
   int g = b200_num_sms();  // every block spins on flags: one block per SM, co-resident
-  const long long slice = ((long long)cg->n + cg->nranks - 1) / cg->nranks;
+  const long long slice = ((long long)cg->n + G - 1) / G;
   const long long want = (slice + VEC_THREADS - 1) / VEC_THREADS;
   if (want < g) g = (int)(want < 1 ? 1 : want);
-  k_cgx_iteration<<<g, VEC_THREADS, 0, st>>>(cg->n, pv, seq, 0, cg->P != nullptr, cg->d_rx, cg->d_M, cg->d_p,
+  k_cgx_iteration<<<g, VEC_THREADS, 0, st>>>(cg->n, pv, seq, cg->P != nullptr, cg->d_rx, cg->d_M, cg->d_p,
                                              cg->d_Gp, d_x, cg->d_r, cg->d_z, cg->d_ctl, cg->d_partials,
                                              cg->d_counter);
   b200_count_launch(1);

@@ -84,7 +84,9 @@ extern "C" int scs_b200_comm_init(int rank, int nranks, const char *id128) {
   g_nranks = nranks;
   return 0;
 }
+static void p2p_teardown(void);
 extern "C" int scs_b200_comm_finalize(void) {
+  p2p_teardown();
   if (g_comm) {
     b200_sync();
     N.CommDestroy(g_comm);
@@ -120,14 +122,15 @@ extern "C" int b200_allgatherv(double *d_buf, const int *offsets) {
 // Peer-memory exchange buffers (NVLink P2P through CUDA IPC) for the fused "sum the partial
 // A_g' z over the ranks + R_x p + p'Gp" kernel of the row-sharded CG (kernels/cg.cu). Each rank
 // owns ONE allocation: red[2][n] doubles (double-buffered partials), rs[2][n] doubles (its slice of
-// the reduced vector, two-phase mode) and a line of 64 flags (slots 0..7 "partial ready" per peer,
-// 8..15 "slice ready" per peer); every rank maps the allocation of every other rank. The handles travel in one
+// the reduced vector, two-phase mode), p[n] and inbox[G][ceil(n/G)] (sharded-x push mode, kernels/cg.cu) and a line
+// of 64 flags (slots 0..7 "partial ready" per peer, 8..15 "slice ready" per peer, 16.. sharded-x) plus 64 scalar
+// slots; every rank maps the allocation of every other rank. The handles travel in one
 // NCCL all-gather at setup; after that the CG inner loop does not call NCCL at all.
 #define P2P_MAX_RANKS 8
 typedef struct {
   int ok, n;
   double *base[P2P_MAX_RANKS];               // base[r]: rank r's allocation as mapped in THIS process
-  unsigned long long *flags[P2P_MAX_RANKS];  // flags[r] = (unsigned long long*)(base[r] + 4 n)
+  unsigned long long *flags[P2P_MAX_RANKS];  // flags[r] = (unsigned long long*)(base[r] + P2P_OFF_FLAGS(n))
 } B200P2p;
 static B200P2p g_p2p;
 static ncclResult_t (*N_AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -139,40 +142,66 @@ extern "C" double *b200_p2p_base(int r) { return g_p2p.base[r]; }
 extern "C" unsigned long long *b200_p2p_flags(int r) { return g_p2p.flags[r]; }
 extern "C" unsigned long long b200_p2p_next_seq(void) { return ++g_p2p_seq; }
 
-extern "C" int b200_p2p_setup(int n) {
+// offsets (in doubles) inside a rank's exchange allocation of stride n
+#define P2P_OFF_P(n) ((size_t)4 * (n))          /* p vector of the sharded-x mode */
+#define P2P_OFF_INBOX(n) ((size_t)5 * (n))      /* inbox [G][ceil(n/G)] */
+#define P2P_OFF_FLAGS(n) ((size_t)6 * (n) + 16) /* 64 flags, then 64 scalar slots */
+extern "C" double *b200_p2p_pvec(int r) { return g_p2p.base[r] + P2P_OFF_P(g_p2p.n); }
+extern "C" double *b200_p2p_inbox(int r) { return g_p2p.base[r] + P2P_OFF_INBOX(g_p2p.n); }
+
+// the exchange p vector can serve ONE workspace at a time (sharded-x mode): claim / release
+static int g_p2p_p_claimed = 0;
+extern "C" int b200_p2p_claim_pvec(void) {
+  if (!g_p2p.ok || g_p2p_p_claimed) return -1;
+  g_p2p_p_claimed = 1;
+  return 0;
+}
+extern "C" void b200_p2p_release_pvec(void) { g_p2p_p_claimed = 0; }
+
+extern "C" int b200_p2p_setup(int n_req) {
   if (g_nranks <= 1 || g_nranks > P2P_MAX_RANKS) return -1;
-  if (g_p2p.ok && g_p2p.n >= n) return 0;
-  if (g_p2p.ok) return -1;  // one size per process (all workspaces of a process share n in practice)
+  if (g_p2p.ok && g_p2p.n >= n_req) return 0;
+  if (g_p2p.ok) return -1;  // one allocation per process, sized generously below; larger systems use NCCL
+  // stride of the allocation: at least 2^23 doubles, so that the workspaces of different sizes a process creates one
+  // after the other (tests, bench.py) share it; 6 x 64 MB = 384 MB of the 180 GB
+  const int n = n_req > (1 << 23) ? n_req : (1 << 23);
+  // Every rank reaches the two collectives below whatever happens locally (an early return on one
+  // rank -- SCS_B200_P2P=0 set for it alone, a failed allocation -- would leave the others blocked in NCCL):
+  // local failures only clear `can_try`, and the final agreement makes all ranks fall back together.
+  int can_try = 1;
   const char *e = getenv("SCS_B200_P2P");
-  if (e && atoi(e) == 0) return -1;
+  if (e && atoi(e) == 0) can_try = 0;
   if (!N_AllGather) *(void **)(&N_AllGather) = dlsym(N.h, "ncclAllGather");
-  if (!N_AllGather) return -1;
+  if (!N_AllGather) return -1;  // same library on every rank: a uniform outcome
   cudaStream_t st = (cudaStream_t)b200_stream();
-  const size_t bytes = ((size_t)4 * n + 64 + 64) * 8;  // + 64 flags + 64 scalar slots (staged sharded-x mode)
-  double *mine = (double *)b200_malloc(bytes);
-  if (!mine) return -1;
-  if (b200_memset0(mine, bytes) != 0) return -1;
+  const size_t bytes = (P2P_OFF_FLAGS(n) + 64 + 64) * 8;
+  double *mine = can_try ? (double *)b200_malloc(bytes) : nullptr;
   cudaIpcMemHandle_t h;
-  if (cudaIpcGetMemHandle(&h, mine) != cudaSuccess) { cudaGetLastError(); b200_free(mine); return -1; }
-  // all-gather the 64-byte handles through NCCL (device buffers)
+  memset(&h, 0, sizeof(h));
+  if (!mine || b200_memset0(mine, bytes) != 0) can_try = 0;
+  if (can_try && cudaIpcGetMemHandle(&h, mine) != cudaSuccess) { cudaGetLastError(); can_try = 0; }
+  // all-gather the 64-byte handles through NCCL (device buffers); a rank that cannot try sends zeros
   char *d_all = (char *)b200_malloc((size_t)g_nranks * sizeof(h));
   std::vector<cudaIpcMemHandle_t> all(g_nranks);
   int rc = -1;
+  std::vector<void *> opened;
   if (d_all && cudaMemcpyAsync(d_all + (size_t)g_rank * sizeof(h), &h, sizeof(h), cudaMemcpyHostToDevice, st) == cudaSuccess &&
       N_AllGather(d_all + (size_t)g_rank * sizeof(h), d_all, sizeof(h), /*ncclChar*/ 0, g_comm, st) == 0 &&
       cudaMemcpyAsync(all.data(), d_all, (size_t)g_nranks * sizeof(h), cudaMemcpyDeviceToHost, st) == cudaSuccess &&
-      cudaStreamSynchronize(st) == cudaSuccess) {
+      cudaStreamSynchronize(st) == cudaSuccess && can_try) {
     rc = 0;
     for (int r = 0; r < g_nranks && rc == 0; ++r) {
       void *p = mine;
-      if (r != g_rank &&
-          cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-        cudaGetLastError();
-        rc = -1;
-        break;
+      if (r != g_rank) {
+        if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          rc = -1;
+          break;
+        }
+        opened.push_back(p);
       }
       g_p2p.base[r] = (double *)p;
-      g_p2p.flags[r] = (unsigned long long *)((double *)p + (size_t)4 * n);
+      g_p2p.flags[r] = (unsigned long long *)((double *)p + P2P_OFF_FLAGS(n));
     }
   }
   b200_free(d_all);
@@ -189,6 +218,23 @@ extern "C" int b200_p2p_setup(int n) {
     }
     b200_free(d_flag);
   }
-  if (!g_p2p.ok) fprintf(stderr, "scs_b200: peer-memory (CUDA IPC) mapping unavailable, using NCCL all-reduce\n");
+  if (!g_p2p.ok) {
+    for (void *p : opened) cudaIpcCloseMemHandle(p);
+    b200_free(mine);
+    memset(&g_p2p, 0, sizeof(g_p2p));
+    fprintf(stderr, "scs_b200: peer-memory (CUDA IPC) mapping unavailable, using NCCL all-reduce\n");
+  }
   return g_p2p.ok ? 0 : -1;
+}
+
+// close the peer mappings and free this rank's exchange allocation (scs_b200_comm_finalize)
+static void p2p_teardown(void) {
+  if (!g_p2p.ok) return;
+  b200_sync();
+  for (int r = 0; r < g_nranks && r < P2P_MAX_RANKS; ++r) {
+    if (!g_p2p.base[r]) continue;
+    if (r == g_rank) b200_free(g_p2p.base[r]);
+    else cudaIpcCloseMemHandle(g_p2p.base[r]);
+  }
+  memset(&g_p2p, 0, sizeof(g_p2p));
 }

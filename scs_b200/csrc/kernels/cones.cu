@@ -334,6 +334,84 @@ k_psd_reconstruct(int k, int count, const int *__restrict__ off, const double *_
     }
   }
 }
+// Same contraction on the fp64 TENSOR-CORE path: mma.sync.aligned.m8n8k4.row.col.f64 (DMMA; SASS "DMMA").
+// tcgen05 has no fp64 MMA kind, so this is the tensor pipe an fp64 contraction at 1e-13 parity can use on sm_100a
+// (north_star: "tensor-core GEMM for the dense Z+ Z+' contraction", reference cones.c:1058-1062 dsyrk).
+// CTA = 4 warps = one 32x32 output tile (ti >= tj) of one block; warp w owns the 16x16 quadrant (w >> 1, w & 1)
+// = 2 x 2 mma tiles. Fragments (PTX ISA, m8n8k4 .f64): A[g][t], B[t][g], C[g][2t], C[g][2t+1] with g = lane >> 2,
+// t = lane & 3. The shared tiles are padded to a row stride of 36 doubles: the 16 lanes of a half-warp then read 16
+// distinct 8-byte banks. Eigenvalues arrive in ascending order (syevd): column chunks whose largest eigenvalue is
+// <= 0 contribute nothing and are skipped.
+#define PTD 36
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(128)
+k_psd_reconstruct_dmma(int k, int count, const int *__restrict__ off, const double *__restrict__ mats,
+                       const double *__restrict__ evals, double *__restrict__ x, const double *sv,
+                       const double *ry) {
+  __shared__ double sA[PT][PTD];  // V[i0+ii, c0+cc] * max(lambda_c, 0)
+  __shared__ double sB[PT][PTD];  // V[j0+jj, c0+cc]
+  const int b = blockIdx.z;
+  const int ti = blockIdx.y, tj = blockIdx.x;
+  if (tj > ti) return;
+  const double *V = mats + (size_t)b * k * k;
+  const double *lam = evals + (size_t)b * k;
+  const int i0 = ti * PT, j0 = tj * PT;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wr = (w >> 1) * 16, wc = (w & 1) * 16;
+  double acc[2][2][2];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) acc[a][c][0] = acc[a][c][1] = 0.0;
+  for (int c0 = 0; c0 < k; c0 += PT) {
+    const int clast = (c0 + PT - 1 < k) ? c0 + PT - 1 : k - 1;
+    if (lam[clast] <= 0.0) continue;  // block-uniform: nothing positive in this chunk
+    for (int e = threadIdx.x; e < PT * PT; e += blockDim.x) {
+      const int rr = e % PT, cc = e / PT;
+      const int c = c0 + cc;
+      double la = 0.0, va = 0.0, vb = 0.0;
+      if (c < k) {
+        la = lam[c];
+        la = la > 0.0 ? la : 0.0;
+        if (i0 + rr < k) va = V[(size_t)(i0 + rr) + (size_t)c * k];
+        if (j0 + rr < k) vb = V[(size_t)(j0 + rr) + (size_t)c * k];
+      }
+      sA[rr][cc] = va * la;
+      sB[rr][cc] = vb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < PT; kk += 4) {
+      const double a0 = sA[wr + g][kk + t], a1 = sA[wr + 8 + g][kk + t];
+      const double b0 = sB[wc + g][kk + t], b1 = sB[wc + 8 + g][kk + t];
+      dmma_m8n8k4(acc[0][0][0], acc[0][0][1], a0, b0);
+      dmma_m8n8k4(acc[0][1][0], acc[0][1][1], a0, b1);
+      dmma_m8n8k4(acc[1][0][0], acc[1][0][1], a1, b0);
+      dmma_m8n8k4(acc[1][1][0], acc[1][1][1], a1, b1);
+    }
+    __syncthreads();
+  }
+  const double inv_sqrt2 = 1.0 / sqrt(2.0);
+  const long long base = off[b];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int i = i0 + wr + 8 * a + g, j = j0 + wc + 8 * c + 2 * t + q;
+        if (i < k && j < k && i >= j) {
+          const double val = (i == j) ? acc[a][c][q] * inv_sqrt2 : acc[a][c][q];
+          const long long row = base + packed_idx(i, j, k);
+          x[row] = post_scale(val, ry, sv, row);
+        }
+      }
+}
 __global__ void k_psd_order1(int count, const int *__restrict__ off, double *__restrict__ x,
                              const double *sv, const double *ry) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -639,8 +717,15 @@ extern "C" int b200_cones_project_rest(B200Cones *c, double *d_x, const double *
       b200_psd_info_or(g.count, g.d_info, c->d_err);
       const int nt = (k + PT - 1) / PT;
       dim3 rg(nt, nt, g.count);
-      k_psd_reconstruct<<<rg, PT * 8, 0, st>>>(k, g.count, g.d_off, g.d_mats, g.d_evals, d_x, d_s,
-                                               d_ry);
+      static int psd_fma = -1;  // SCS_B200_PSD_FMA=1: the plain fp64 FMA contraction (A/B measurement of the DMMA path)
+      if (psd_fma < 0) {
+        const char *e = getenv("SCS_B200_PSD_FMA");
+        psd_fma = (e && atoi(e) != 0) ? 1 : 0;
+      }
+      if (psd_fma)
+        k_psd_reconstruct<<<rg, PT * 8, 0, st>>>(k, g.count, g.d_off, g.d_mats, g.d_evals, d_x, d_s, d_ry);
+      else
+        k_psd_reconstruct_dmma<<<rg, 128, 0, st>>>(k, g.count, g.d_off, g.d_mats, g.d_evals, d_x, d_s, d_ry);
       b200_count_launch(1);
     }
   }

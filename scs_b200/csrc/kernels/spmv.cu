@@ -415,6 +415,15 @@ spmv_flag_kernel(const int *__restrict__ colidx, const double *__restrict__ vals
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int g_begin = cta_begin[blockIdx.x];  // in groups of SPMV3_NCW warp-tiles
   const int nt = cta_begin[blockIdx.x + 1] - g_begin;
+  // multi-GPU push mode: the routing table (static device data, written once at setup)
+  __shared__ int s_rt_lo[9];
+  __shared__ double *s_rt_dst[8];
+  const bool routed = (POST == B200_POST_NONE) && hook == B200_HOOK_P2P_ROUTE;
+  if (routed && tid < 9) {
+    const B200P2pRoute *rt = reinterpret_cast<const B200P2pRoute *>(hook_arg);
+    s_rt_lo[tid] = tid <= rt->nranks ? rt->lo[tid] : 0x7fffffff;
+    if (tid < 8) s_rt_dst[tid] = tid < rt->nranks ? rt->dst[tid] : nullptr;
+  }
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < SPMV3_STAGES; ++s) {
@@ -603,7 +612,13 @@ spmv_flag_kernel(const int *__restrict__ colidx, const double *__restrict__ vals
             iv0 = (init != nullptr) ? init[row] : 0.0;
           }
           if (init != nullptr) sres = __dadd_rn(sres, init_sign * iv0);
-          spmv_epilogue_pre<POST>(sres, row, y, dv, vv, dot_acc);
+          if (routed) {  // push the row to the rank that owns it (a warp-tile spans at most a few owners)
+            int o = 0;
+            while (row >= s_rt_lo[o + 1]) ++o;
+            s_rt_dst[o][row - s_rt_lo[o]] = sres;
+          } else {
+            spmv_epilogue_pre<POST>(sres, row, y, dv, vv, dot_acc);
+          }
         }
       }
       __syncwarp();  // the scratch is rewritten by the next warp-tile
@@ -611,18 +626,25 @@ spmv_flag_kernel(const int *__restrict__ colidx, const double *__restrict__ vals
   }
 
   if (skipped) return;  // uniform over the CTA: every thread read the same *skip after the predecessor completed
-  if (hook == B200_HOOK_P2P_SIGNAL) {
-    // multi-GPU: tell every peer that this rank's partial product is complete (last block only)
+  if (hook == B200_HOOK_P2P_SIGNAL || routed) {
+    // multi-GPU: tell every peer that this rank's partial product is complete (last block only). In push mode the
+    // rows were stored into PEER memory: every block orders its stores system-wide before it takes its ticket.
     __syncthreads();
     if (threadIdx.x == 0) {
-      __threadfence();
+      if (routed) __threadfence_system(); else __threadfence();
       const unsigned tk = atomicAdd(counter, 1u);
       if (tk == gridDim.x - 1) {
         *counter = 0u;
         __threadfence_system();
-        const B200P2pSignal *ps = reinterpret_cast<const B200P2pSignal *>(hook_arg);
-        for (int r = 0; r < ps->nranks; ++r)
-          if (r != ps->rank) *((volatile unsigned long long *)(ps->flags[r] + ps->rank)) = hook_val;
+        if (routed) {
+          const B200P2pRoute *rt = reinterpret_cast<const B200P2pRoute *>(hook_arg);
+          for (int r = 0; r < rt->nranks; ++r)
+            if (r != rt->rank) *((volatile unsigned long long *)(rt->flags[r] + rt->rank)) = hook_val;
+        } else {
+          const B200P2pSignal *ps = reinterpret_cast<const B200P2pSignal *>(hook_arg);
+          for (int r = 0; r < ps->nranks; ++r)
+            if (r != ps->rank) *((volatile unsigned long long *)(ps->flags[r] + ps->rank)) = hook_val;
+        }
       }
     }
   }
@@ -1196,6 +1218,11 @@ extern "C" int b200_spmv(const B200Spmv *M, const B200SpmvArgs *a) {
                           (const int4 *)M->d_wt3, (const int *)M->d_cta_begin3, TAIL));        \
     else spmv_ws_kernel<POSTV><<<grid, block, smem, st>>>(ARGS);                               \
   } while (0)
+  if (a->hook == B200_HOOK_P2P_ROUTE && !(M->version == 3 && M->d_vptr == nullptr && a->post == B200_POST_NONE)) {
+    b200_set_error("b200_spmv: B200_HOOK_P2P_ROUTE needs the one-pass flagged-stream kernel with POST_NONE",
+                   cudaErrorInvalidValue, __FILE__, __LINE__);
+    return -1;
+  }
   if (M->version == 3 && M->d_vptr != nullptr) {
     // long-row mode: sums per virtual row, then the combine pass with the real epilogue
     spmv_flag_kernel<B200_POST_NONE><<<grid, block, smem, st>>>(
@@ -1235,6 +1262,8 @@ extern "C" int b200_spmv(const B200Spmv *M, const B200SpmvArgs *a) {
   return 0;
 }
 extern "C" int b200_spmv_version(const B200Spmv *M) { return M->version; }
+// B200_HOOK_P2P_ROUTE needs the one-pass flagged-stream kernel (no virtual rows / combine pass)
+extern "C" int b200_spmv_can_route(const B200Spmv *M) { return M && M->version == 3 && M->d_vptr == nullptr; }
 extern "C" long long b200_spmv_stored(const B200Spmv *M) { return M->stored; }
 
 // Alternating launches of two operators (A then A'), every launch bracketed by its own CUDA

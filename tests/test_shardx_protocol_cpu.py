@@ -1,13 +1,15 @@
-"""CPU emulation of the STAGED "sharded-x" multi-GPU CG iteration (scs_b200/csrc/kernels/cg.cu:
-k_cgx_iteration + cg_iteration_shard_x). Every rank is a Python thread; exchange allocations, flag lines
-and scalar slots are shared numpy arrays laid out exactly like the device buffers (partials red[2][n],
-p-exchange [2][n] at offset 2n, flag slots 0.. "partial", 16.. / 24.. "scalars of round 1 / 2", 32.. "p slice",
-scalar slots [round][parity][rank][2]). The emulation follows the kernel phase by phase -- same slot
-arithmetic, same double-buffering by the parity of seq, same rank-order sums, same stop logic -- and checks:
-no deadlock, all ranks hold bit-identical p / alpha / beta / stop decisions, and the iterates agree with a
-plain single-process preconditioned CG on the same operator (reference linsys/cpu/indirect/private.c:133-217).
+"""CPU emulation of the PUSH-based "sharded-x" multi-GPU CG iteration (scs_b200/csrc/kernels/cg.cu:
+k_cgx_iteration + cg_iteration_shard_x, scs_b200/csrc/kernels/spmv.cu B200_HOOK_P2P_ROUTE). Every rank is a Python
+thread; the exchange allocations (inbox [G][S], the p vector), flag lines and scalar slots are shared numpy arrays laid
+out like the device buffers (flag slots 0.. "partial", 16.. / 24.. "scalars of round 1 / 2", 32.. "p slice", scalar
+slots [round][parity][rank][2]). Data moves only by STORES into the peer's arrays, exactly as on the device: the K2
+SpMV pushes each output row into the owner's inbox, K4 stores the new p slice into every rank's p. The emulation
+follows the kernel phase by phase -- same slot arithmetic, same rank-order sums, same stop logic, NO double buffering
+of inbox / p -- and checks: no deadlock, no torn reads under random delays (ranks run up to an iteration apart), all
+ranks hold bit-identical p / alpha / beta / stop decisions, and the iterates agree with a plain single-process
+preconditioned CG on the same operator (reference linsys/cpu/indirect/private.c:133-217).
 It validates the PROTOCOL (what the blocks of one rank do together is one thread here); the CUDA-level parts
-(fences, co-residency) remain for the first multi-GPU run."""
+(fences, co-residency) are for the multi-GPU run (tests/mgpu_check.py)."""
 import threading
 import time
 
@@ -28,7 +30,8 @@ class Rank(threading.Thread):
         self.x = np.zeros(n)
         self.r = b.copy()
         self.z = self.r * M
-        self.p = self.z.copy()
+        self.p = shared["p"][me]            # the rank's p lives in its exchange allocation: peers store into it
+        self.p[:] = self.z
         self.Gp = np.zeros(n)
         self.ctl = dict(ztr=float(self.z @ self.r), rnorm=float(np.abs(self.r).max()), iters=0, done=0,
                         alpha=0.0, beta=0.0)
@@ -61,22 +64,24 @@ class Rank(threading.Thread):
         if self.ctl["done"]:
             return
         parity = seq & 1
-        slot = parity * n
-        pex = 2 * n + slot
         lo, hi = self.lo, self.hi
-        # K1 / K2: the rank's partial into its exchange buffer, then "partial ready" to the peers
+        S = (n + G - 1) // G
+        # K1 / K2: the rank's partial, every output row PUSHED into the inbox of its owner (lane `me`), then
+        # "partial ready" to the peers
         part = self.A.T @ (self.d * (self.A @ self.p))
-        sh["buf"][me][slot:slot + n] = part
+        for q in range(G):
+            qlo, qhi = n * q // G, n * (q + 1) // G
+            sh["inbox"][q][me * S:me * S + (qhi - qlo)] = part[qlo:qhi]
         for q in range(G):
             if q != me:
                 sh["flags"][q][me] = seq
         ztr_old, iters_old = self.ctl["ztr"], self.ctl["iters"]
         self.pause()
-        # 1: wait for the partials, reduce my slice in rank order
+        # 1: wait for the peers' partials, reduce my slice from MY inbox in rank order
         self.wait(0, me, seq)
         s = np.zeros(hi - lo)
         for q in range(G):
-            s = s + sh["buf"][q][slot + lo:slot + hi]
+            s = s + sh["inbox"][me][q * S:q * S + (hi - lo)]
         self.Gp[lo:hi] = self.rx[lo:hi] * self.p[lo:hi] + s
         mine = float(self.p[lo:hi] @ self.Gp[lo:hi])
         for q in range(G):
@@ -122,26 +127,21 @@ class Rank(threading.Thread):
             if iters_old + 1 >= self.max_its:
                 done = 1
         self.pause()
-        # 5: K4 on the slice, publish the p slice
+        # 5: K4 on the slice, stored into EVERY rank's p
         if not done:
             pn = self.z[lo:hi] + beta * self.p[lo:hi]
-            self.p[lo:hi] = pn
-            sh["buf"][me][pex + lo:pex + hi] = pn
+            for q in range(G):
+                sh["p"][q][lo:hi] = pn
         self.ctl.update(ztr=ztr, rnorm=rn, iters=iters_old + 1, alpha=alpha, beta=beta if not done else self.ctl["beta"],
                         done=done)
         for q in range(G):
             sh["flags"][q][32 + me] = seq
         self.history.append((alpha, beta, ztr, rn, done))
         self.pause()
-        # 6: the other slices of the new p
+        # 6: the peers' slices of the new p have landed
         if done:
             return
-        self.wait(32, -1, seq)
-        for q in range(G):
-            if q == me:
-                continue
-            qlo, qhi = n * q // G, n * (q + 1) // G
-            self.p[qlo:qhi] = sh["buf"][q][pex + qlo:pex + qhi]
+        self.wait(32, me, seq)
 
     def run(self):
         try:
@@ -189,7 +189,9 @@ def test_sharded_x_protocol(G, n, m, iters, tol, jitter):
     Mdiag = 1.0 / (rx + np.asarray((A.multiply(A)).T @ d).ravel())
     b = rng.standard_normal(n)
     offs = [m * g // G for g in range(G + 1)]           # contiguous row blocks
-    shared = {"buf": [np.zeros(4 * n) for _ in range(G)], "flags": [np.zeros(64, dtype=np.uint64) for _ in range(G)],
+    S = (n + G - 1) // G
+    shared = {"inbox": [np.zeros(G * S) for _ in range(G)], "p": [np.zeros(n) for _ in range(G)],
+              "flags": [np.zeros(64, dtype=np.uint64) for _ in range(G)],
               "scal": [np.zeros(64) for _ in range(G)], "jitter": jitter}
     max_its = 10 * n
     ranks = [Rank(g, G, n, A[offs[g]:offs[g + 1]], d[offs[g]:offs[g + 1]], rx, Mdiag, b, shared, iters, tol, max_its)
@@ -204,7 +206,7 @@ def test_sharded_x_protocol(G, n, m, iters, tol, jitter):
     # all ranks: identical scalars and decisions, bit for bit, and identical p after every completed iteration
     for r in ranks[1:]:
         assert r.history == ranks[0].history
-        assert np.array_equal(r.p, ranks[0].p)
+        assert np.array_equal(np.asarray(r.p), np.asarray(ranks[0].p))
         assert r.ctl == ranks[0].ctl
     # x is owned by slices: assemble it and compare with the single-process PCG
     x = np.concatenate([r.x[r.lo:r.hi] for r in ranks])

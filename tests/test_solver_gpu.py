@@ -248,14 +248,53 @@ def test_max_iters_and_warm_start(lib):
     lib.scs_finish(w)
 
 
-def test_unsupported_cone_fails_loudly(lib):
+def test_malformed_cone_fails_loudly(lib):
     prob = small_problem("lp", seed=1)
-    cone = dict(prob["cone"])
-    cone["l"] -= 4
-    cone["cs"] = [2]          # complex PSD cone of order 2 = 4 rows: staged, refused unless SCS_B200_COMPLEX_PSD=1
-    hp = capi.HostProblem(prob["A"], prob["b"], prob["c"], cone)
+    hp = capi.HostProblem(prob["A"], prob["b"], prob["c"], prob["cone"])
+    hp.cone.l -= 4
+    hp.cone.cssize = 1          # claims one complex PSD block but gives no array: scs_init must refuse (no crash)
     st = capi.default_settings(lib, verbose=0)
     assert not lib.scs_init(C.byref(hp.data), C.byref(hp.cone), C.byref(st))
+
+
+def test_complex_psd_cone_matches_reference(lib, reflib):
+    """Complex (Hermitian) PSD blocks in the device loop (kernels/cones_complex.cu; reference cones.c:1072-1156), mixed
+    with every other dense cone type. The known optimum is built with the reference's own dual-cone projection:
+    y = Pi_K*(z), s = y - z, b = A x + s, c = -A'y (same construction as test/problem_utils.h:22-81)."""
+    cone = {"z": 3, "l": 10, "q": [4, 9], "s": [3, 5], "cs": [2, 5, 4, 1]}
+    m = capi.cone_rows(cone)
+    n = 40
+    rng = np.random.default_rng(77)
+    A = problems.random_sparse_csc(m, n, 9, rng)
+    reflib._scs_init_cone.restype = C.c_void_p
+    reflib._scs_init_cone.argtypes = [C.POINTER(capi.ScsCone), C.c_int]
+    reflib._scs_proj_dual_cone.restype = C.c_int
+    reflib._scs_proj_dual_cone.argtypes = [capi.c_double_p, C.c_void_p, C.c_void_p, capi.c_double_p]
+    reflib._scs_finish_cone.argtypes = [C.c_void_p]
+    k, keep = capi.make_cone(cone)
+    cw = reflib._scs_init_cone(C.byref(k), m)
+    zz = rng.uniform(-1, 1, m)
+    y = zz.copy()
+    assert reflib._scs_proj_dual_cone(capi.dptr(y), cw, None, None) == 0
+    reflib._scs_finish_cone(cw)
+    sv = y - zz
+    x0 = rng.uniform(-1, 1, n)
+    prob = {"A": A, "b": problems.csc_matvec(A, x0) + sv, "c": -problems.csc_rmatvec(A, y), "cone": cone}
+    opt = float(prob["c"] @ x0)
+    st_m, info_m, x, yy, s = solve_with(lib, prob, max_iters=1)
+    st_r, info_r, xr, yr, sr = solve_with(reflib, prob, max_iters=1)
+    assert st_m == st_r and info_m.iter == info_r.iter == 1
+    for a, b, nm in ((x, xr, "x"), (yy, yr, "y"), (s, sr, "s")):
+        err = np.abs(a - b).max() / max(1.0, np.abs(b).max())
+        assert err <= 1e-10, (nm, err)
+    eps = 1e-7
+    st_m, info_m, x, yy, s = solve_with(lib, prob, eps_abs=eps, eps_rel=eps, max_iters=50000)
+    st_r, info_r, xr, yr, sr = solve_with(reflib, prob, eps_abs=eps, eps_rel=eps, max_iters=50000)
+    print(f"\n[complex PSD] mine it={info_m.iter} pobj={info_m.pobj:.10e} | ref it={info_r.iter} pobj={info_r.pobj:.10e} "
+          f"| known optimum {opt:.10e}")
+    assert st_m == st_r == 1
+    assert abs(info_m.pobj - info_r.pobj) <= 100 * eps * max(1.0, abs(info_r.pobj))
+    assert abs(info_m.pobj - opt) <= 1000 * eps * max(1.0, abs(opt))
 
 
 def test_infeasible_and_unbounded(lib, reflib):

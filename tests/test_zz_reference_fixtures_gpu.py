@@ -91,8 +91,7 @@ def test_exp_power_operator_matches_committed_goldens(lib):
 
 
 def test_complex_psd_operator_matches_reference(lib, reflib, monkeypatch):
-    """staged complex-PSD kernels (kernels/cones_complex.cu, opt-in) against the reference's zheevr projection"""
-    monkeypatch.setenv("SCS_B200_COMPLEX_PSD", "1")
+    """complex-PSD kernels (kernels/cones_complex.cu) against the reference's zheevr projection"""
     reflib._scs_init_cone.restype = C.c_void_p
     reflib._scs_init_cone.argtypes = [PP(capi.ScsCone), C.c_int]
     reflib._scs_proj_dual_cone.argtypes = [capi.c_double_p, C.c_void_p, C.c_void_p, capi.c_double_p]

@@ -678,6 +678,38 @@ static void fill_nan(double *v, int len) {
   for (i = 0; i < len; ++i) v[i] = NAN;
 }
 
+/* Ctrl-C handling, same contract as the reference (src/ctrlc.c:84-126, src/scs.c:1344,1400-1403,1482): a SIGINT
+ * handler is installed for the duration of scs_solve (reference counted, the previous handler is restored) and the
+ * iteration polls the flag -- here once per ADMM iteration on the host, between two enqueues -- returning SCS_SIGINT. */
+#include <pthread.h>
+#include <signal.h>
+static volatile sig_atomic_t int_detected;
+static struct sigaction int_oact;
+static pthread_mutex_t int_mutex = PTHREAD_MUTEX_INITIALIZER;
+static int int_listeners = 0;
+static void handle_ctrlc(int sig) { int_detected = sig ? sig : -1; }
+static void start_interrupt_listener(void) {
+  pthread_mutex_lock(&int_mutex);
+  if (int_listeners == 0) {
+    struct sigaction act;
+    int_detected = 0;
+    act.sa_flags = 0;
+    sigemptyset(&act.sa_mask);
+    act.sa_handler = handle_ctrlc;
+    sigaction(SIGINT, &act, &int_oact);
+  }
+  int_listeners++;
+  pthread_mutex_unlock(&int_mutex);
+}
+static void end_interrupt_listener(void) {
+  pthread_mutex_lock(&int_mutex);
+  if (int_listeners > 0 && --int_listeners == 0) {
+    struct sigaction act;
+    sigaction(SIGINT, &int_oact, &act);
+  }
+  pthread_mutex_unlock(&int_mutex);
+}
+
 static int failure(ScsWork *w, int m, int n, ScsSolution *sol, ScsInfo *info, int status,
                    const char *msg, const char *ststr) {
   if (info) {
@@ -703,6 +735,7 @@ static int failure(ScsWork *w, int m, int n, ScsSolution *sol, ScsInfo *info, in
   }
   (void)w;
   printf("Failure:%s\n", msg);
+  end_interrupt_listener(); /* every failure() inside scs_solve leaves the solve; outside it the count is 0: no-op */
   return status;
 }
 
@@ -843,6 +876,7 @@ scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_int warm_star
   stgs = w->stgs;
   stgs->warm_start = warm_start;
   t_solve = now_ms();
+  start_interrupt_listener();
   strcpy(info->lin_sys_solver, scs_get_lin_sys_method());
   info->status_val = SCS_UNFINISHED;
   cg0 = w->p->tot_cg_its;
@@ -861,6 +895,8 @@ scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_int warm_star
   for (i = 0; i < stgs->max_iters; ++i) {
     const int check = (i % CONVERGED_INTERVAL == 0);
     int dual_done = 0;
+    if (int_detected) /* reference scs.c:1400-1403 */
+      return failure(w, w->m, w->n, sol, info, SCS_SIGINT, "interrupted", "interrupted");
     /* ---- Anderson acceleration (scs.c:1359-1366) */
     if (w->accel) {
       if (i > 0 && i % stgs->acceleration_interval == 0) {
@@ -946,6 +982,7 @@ scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_int warm_star
   w->stat_cg_iters = w->p->tot_cg_its - cg0;
   w->stat_solves = w->p->n_solves - solves0;
   w->stat_launches = b200_launches() - launches0;
+  end_interrupt_listener();
   if (stgs->verbose) {
     int k;
     for (k = 0; k < 78; ++k) printf("-");

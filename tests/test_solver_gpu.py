@@ -297,6 +297,28 @@ def test_complex_psd_cone_matches_reference(lib, reflib):
     assert abs(info_m.pobj - opt) <= 1000 * eps * max(1.0, abs(opt))
 
 
+def test_sigint_stops_a_long_solve(lib):
+    """Ctrl-C contract of the reference (src/ctrlc.c, src/scs.c:1400-1403): SIGINT during scs_solve ends it with
+    SCS_SIGINT (-5) / status "interrupted", NaN solution, and the previous handler is restored afterwards."""
+    import os
+    import signal
+    import threading
+    prob = small_problem("socp", seed=9)
+    before = signal.getsignal(signal.SIGINT)
+    t = threading.Timer(0.5, lambda: os.kill(os.getpid(), signal.SIGINT))
+    t.start()
+    try:
+        st, info, x, y, s = solve_with(lib, prob, eps_abs=0.0, eps_rel=0.0, eps_infeas=0.0, max_iters=100000000)
+    finally:
+        t.cancel()
+    assert st == -5, (st, info.status)
+    assert info.status.decode() == "interrupted" and info.iter == -1 and np.isnan(x).all()
+    assert signal.getsignal(signal.SIGINT) == before
+    # and the library still works
+    st, info, *_ = solve_with(lib, prob)
+    assert st == 1
+
+
 def test_infeasible_and_unbounded(lib, reflib):
     """status codes on certificates (reference test/problems/infeasible_socp.h, unbounded_socp.h)"""
     rng = np.random.default_rng(2)

@@ -49,6 +49,10 @@ typedef struct B200Spmv B200Spmv;
 B200Spmv *b200_spmv_create(int nrows, int ncols, const int *h_rowptr, const int *h_colidx,
                            const double *h_vals);
 void b200_spmv_destroy(B200Spmv *M);
+/* both resident orientations built ON THE DEVICE from the host CSC of A (kernels/setup.cu): 0 ok, 1 declined (use the
+ * host builders: rows longer than a warp-tile, forced v2, SCS_B200_HOST_SETUP=1), < 0 CUDA error */
+int b200_setup_ops_from_csc(int m, int n, const int *h_Ap, const int *h_Ai, const double *h_Ax, B200Spmv **A_out,
+                            B200Spmv **At_out);
 int b200_spmv_nrows(const B200Spmv *M);
 int b200_spmv_ncols(const B200Spmv *M);
 long long b200_spmv_nnz(const B200Spmv *M);
@@ -96,6 +100,13 @@ typedef struct {
                             prologue -- barrier init, first matrix stages -- overlaps that kernel's tail) */
 } B200SpmvArgs;
 
+/* reordered copies for the CG operator (kernels/spmv.cu, kernels/setup.cu): rows of A by smallest column index */
+B200Spmv *b200_spmv_permuted_rows(const B200Spmv *M, const int *d_perm /* new -> old */);
+int b200_spmv_refresh_permuted(B200Spmv *Mp, const B200Spmv *M, const int *d_perm); /* values only */
+B200Spmv *b200_spmv_renumbered_cols(const B200Spmv *M, const int *d_inv /* old -> new */); /* view: borrows M's arrays */
+int b200_perm_rows_by_min_col(const B200Spmv *A, int *d_perm, int *d_inv);
+int b200_gather_vec(int n, const int *d_perm, const double *d_src, double *d_dst); /* dst[i] = src[perm[i]] */
+
 int b200_spmv(const B200Spmv *M, const B200SpmvArgs *a);
 int b200_spmv_can_route(const B200Spmv *M); /* 1: B200_HOOK_P2P_ROUTE is available for this operator */
 /* per-launch CUDA-event timing of M0 and M1 launched alternately (cold L2), ms per launch */
@@ -119,6 +130,10 @@ typedef struct {
   const B200Spmv *A;   /* CSR of A  (m x n): rows of A   -> used for z = A p      */
   const B200Spmv *At;  /* CSR of A' (n x m): cols of A   -> used for y = A' z     */
   const B200Spmv *P;   /* full symmetric P as CSR (n x n) or NULL                 */
+  /* optional m-space-reordered pair used ONLY inside mat_vec (tmp lives in the permuted order): A_cg = rows of A
+   * sorted by smallest column, At_cg = A' with its column indices renumbered, d_ry_cg = R_y in that order */
+  const B200Spmv *A_cg, *At_cg;
+  const double *d_ry_cg;
   const double *d_rx;  /* R_x (n) */
   const double *d_ry;  /* R_y (m) */
   double *d_M;         /* Jacobi preconditioner (n) */

@@ -248,9 +248,50 @@ static int restrict_rows(int n, const int *Ap, const int *Ai, const double *Ax, 
   return 0;
 }
 
+#include <time.h>
+static double wall_ms(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+}
+/* SCS_B200_SETUP_TIMING=1: wall-clock breakdown of the setup on stderr (syncs the stream at every mark) */
+static void setup_mark(const char *what, double *t_last) {
+  if (!getenv("SCS_B200_SETUP_TIMING")) return;
+  b200_sync();
+  {
+    const double t = wall_ms();
+    fprintf(stderr, "scs_b200 setup: %-44s %8.1f ms\n", what, t - *t_last);
+    *t_last = t;
+  }
+}
+
+/* The reordered pair used inside the CG operator (kernels/spmv.cu "Reordered copies"): built once, values and R_y
+ * refreshed whenever the resident operators may have been rescaled (b200_linsys_update_diag_r_dev). */
+static int cg_ops_build(ScsLinSysWork *w) {
+  const char *e = getenv("SCS_B200_REORDER");
+  if (w->nranks > 1 || (e && atoi(e) == 0)) return 0;
+  if (!b200_spmv_can_route(w->A) || !b200_spmv_can_route(w->At)) return 0; /* one-pass flagged streams only */
+  w->d_perm = (int *)b200_malloc((size_t)w->m * 4);
+  w->d_inv = (int *)b200_malloc((size_t)w->m * 4);
+  w->d_ry_cg = (double *)b200_malloc((size_t)w->m * 8);
+  if (!w->d_perm || !w->d_inv || !w->d_ry_cg) return -1;
+  if (b200_perm_rows_by_min_col(w->A, w->d_perm, w->d_inv) != 0) return -1;
+  w->A_cg = b200_spmv_permuted_rows(w->A, w->d_perm);
+  w->At_cg = b200_spmv_renumbered_cols(w->At, w->d_inv);
+  if (!w->A_cg || !w->At_cg) return -1;
+  w->cg.A_cg = w->A_cg; w->cg.At_cg = w->At_cg; w->cg.d_ry_cg = w->d_ry_cg;
+  return 0;
+}
+static int cg_ops_refresh(ScsLinSysWork *w) {
+  if (!w->A_cg) return 0;
+  if (b200_spmv_refresh_permuted(w->A_cg, w->A, w->d_perm) != 0) return -1;
+  return b200_gather_vec(w->m, w->d_perm, w->d_diag_r + w->n, w->d_ry_cg);
+}
+
 ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
                                      const scs_float *diag_r) {
   ScsLinSysWork *w;
+  double t_mark = wall_ms();
   int *Tp = NULL, *Ti = NULL;
   double *Tx = NULL;
   int *Lp = NULL, *Li = NULL;
@@ -281,10 +322,20 @@ ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
     w->A = b200_spmv_create(w->mloc, n, Tp, Ti, Tx);
     free(Lp); free(Li); free(Lx);
   } else {
-    /* CSR of A' is the CSC of A as given */
-    w->At = b200_spmv_create(n, m, A->p, A->i, A->x);
-    if (transpose_csc(m, n, A->p, A->i, A->x, &Tp, &Ti, &Tx) != 0) goto fail;
-    w->A = b200_spmv_create(m, n, Tp, Ti, Tx);
+    /* device path first: upload the CSC once, transpose by a stable radix sort, build both flagged streams there */
+    const int rc_dev = b200_setup_ops_from_csc(m, n, A->p, A->i, A->x, &w->A, &w->At);
+    if (rc_dev < 0) goto fail;
+    if (rc_dev == 0) {
+      setup_mark("linsys: both operators built on the device", &t_mark);
+    } else {
+      /* host builders: CSR of A' is the CSC of A as given */
+      w->At = b200_spmv_create(n, m, A->p, A->i, A->x);
+      setup_mark("linsys: operator A' (host plan + upload)", &t_mark);
+      if (transpose_csc(m, n, A->p, A->i, A->x, &Tp, &Ti, &Tx) != 0) goto fail;
+      setup_mark("linsys: host transpose", &t_mark);
+      w->A = b200_spmv_create(m, n, Tp, Ti, Tx);
+      setup_mark("linsys: operator A (host plan + upload)", &t_mark);
+    }
   }
   free(Tp); free(Ti); free(Tx);
   if (!w->A || !w->At) goto fail;
@@ -364,6 +415,9 @@ ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
   if (b200_h2d(w->d_diag_r, diag_r, ((size_t)n + m) * 8) != 0) goto fail;
   if (b200_cg_set_preconditioner(&w->cg, w->d_Pdiag) != 0) goto fail;
   if (b200_sync() != 0) goto fail;
+  setup_mark("linsys: vectors, preconditioner", &t_mark);
+  if (cg_ops_build(w) != 0 || cg_ops_refresh(w) != 0 || b200_sync() != 0) goto fail;
+  setup_mark("linsys: reordered pair for the CG operator", &t_mark);
   return w;
 fail:
   fprintf(stderr, "scs_b200: init_lin_sys_work failed: %s\n", b200_last_error());
@@ -374,6 +428,11 @@ fail:
 void scs_free_lin_sys_work(ScsLinSysWork *w) {
   if (!w) return;
   b200_sync();
+  b200_spmv_destroy(w->At_cg); /* a view of At: before At itself */
+  b200_spmv_destroy(w->A_cg);
+  b200_free(w->d_ry_cg);
+  b200_free(w->d_perm);
+  b200_free(w->d_inv);
   b200_spmv_destroy(w->A);
   b200_spmv_destroy(w->At);
   b200_spmv_destroy(w->P);
@@ -438,6 +497,7 @@ int b200_linsys_update_diag_r_dev(ScsLinSysWork *w, const double *d_diag_r) {
   if (d_diag_r != w->d_diag_r) {
     if (b200_d2d(w->d_diag_r, d_diag_r, ((size_t)w->n + w->m) * 8) != 0) return -1;
   }
+  if (cg_ops_refresh(w) != 0) return -1; /* the operators may have been rescaled in place; R_y has changed */
   return b200_cg_set_preconditioner(&w->cg, w->d_Pdiag);
 }
 

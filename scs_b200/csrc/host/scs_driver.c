@@ -325,9 +325,20 @@ static void print_header(const ScsWork *w) {
          (long)w->nnzA, (long)w->nnzP);
 }
 
+static void init_mark(const char *what, double *t_last) {
+  if (!getenv("SCS_B200_SETUP_TIMING")) return;
+  b200_sync();
+  {
+    const double t = now_ms();
+    fprintf(stderr, "scs_b200 setup: %-44s %8.1f ms\n", what, t - *t_last);
+    *t_last = t;
+  }
+}
+
 ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {
   ScsWork *w;
   const double t0 = now_ms();
+  double t_mark = t0;
   int n, m, i, dev_equil = 0;
   size_t l;
   if (!d || !k || !stgs) {
@@ -455,6 +466,7 @@ ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {
     }
   }
   if (i != 0) goto fail;
+  init_mark("init: validate, copies, device vectors", &t_mark);
   if (dev_equil) {
     /* upload the raw A (both orientations), equilibrate in place on the device */
     if (b200_comm_nranks() > 1) {
@@ -464,6 +476,7 @@ ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {
     }
     w->p = scs_init_lin_sys_work(d->A, SCS_NULL, w->h_diag_r);
     if (!w->p) { printf("ERROR: init_lin_sys_work failure\n"); goto fail; }
+    t_mark = now_ms();
     if (b200_comm_nranks() > 1) {
       if (b200_linsys_scale_local(w->p, w->d_D, w->d_E) != 0) goto fail;
     } else if (b200_equilibrate_dev(w->p->A, w->p->At, w->cone_boundaries, w->cone_boundaries_len,
@@ -475,6 +488,7 @@ ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {
         b200_sync() != 0)
       goto fail;
     if (w->k->bsize > 1) normalize_box_cone(w->k, w->D + w->k->z + w->k->l, w->k->bsize);
+    init_mark("init: device equilibration + preconditioner", &t_mark);
   }
   /* b, c: stores *_orig, normalises, uploads */
   memcpy(w->b_orig, d->b, (size_t)m * 8);
@@ -498,6 +512,7 @@ ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {
     if (!w->accel && w->stgs->verbose) printf("WARN: aa_init returned NULL, no acceleration applied.\n");
   }
   if (b200_sync() != 0) goto fail;
+  init_mark("init: b, c, cones, AA workspace", &t_mark);
   w->r_orig.last_iter = w->r_norm.last_iter = -1;
   w->setup_time = now_ms() - t0;
   return w;

@@ -795,14 +795,17 @@ static int mat_vec_sharded(B200Cg *cg, const double *d_x, double *d_y, int with_
 
 static int mat_vec(B200Cg *cg, const double *d_x, double *d_y, int with_dot, const int *d_skip) {
   if (cg->nranks > 1) return mat_vec_sharded(cg, d_x, d_y, with_dot, d_skip);
+  // the m-space-reordered pair when present: tmp is internal to the operator, so its ordering is free
+  const bool re = cg->A_cg != nullptr && cg->At_cg != nullptr && cg->d_ry_cg != nullptr;
+  const B200Spmv *A = re ? cg->A_cg : cg->A, *At = re ? cg->At_cg : cg->At;
   B200SpmvArgs a;
   memset(&a, 0, sizeof(a));
   // K1: tmp = (A x) ./ R_y
   a.pdl = cg_pdl_enabled() ? 1 : 0;
   a.d_x = d_x; a.d_y = cg->d_tmp; a.d_init = nullptr; a.init_sign = 1.0;
-  a.post = B200_POST_DIV; a.d_d = cg->d_ry; a.d_v = nullptr; a.d_dot = nullptr;
+  a.post = B200_POST_DIV; a.d_d = re ? cg->d_ry_cg : cg->d_ry; a.d_v = nullptr; a.d_dot = nullptr;
   a.hook = B200_HOOK_NONE; a.d_hook_arg = nullptr; a.d_skip = d_skip;
-  if (b200_spmv(cg->A, &a) != 0) return -1;
+  if (b200_spmv(A, &a) != 0) return -1;
   const double *init = nullptr;
   if (cg->P) {
     // y = P x first (reference accumulates P x before A' z)
@@ -817,7 +820,7 @@ static int mat_vec(B200Cg *cg, const double *d_x, double *d_y, int with_dot, con
   a.d_d = cg->d_rx; a.d_v = d_x; a.d_dot = with_dot ? &cg->d_ctl->pGp : nullptr;
   a.hook = with_dot ? B200_HOOK_CG_ALPHA : B200_HOOK_NONE;
   a.d_hook_arg = cg->d_ctl; a.d_skip = d_skip;
-  return b200_spmv(cg->At, &a);
+  return b200_spmv(At, &a);
 }
 
 // sharded-x push mode (see k_cgx_iteration): -1 = read SCS_B200_SHARD_X once, 0 = off, 1 = on
@@ -915,13 +918,15 @@ extern "C" int b200_cg_time_kernels(B200Cg *cg, double *d_x, int reps, double *o
       B200SpmvArgs a;
       memset(&a, 0, sizeof(a));
       cudaEventRecord(ev[(size_t)r * 5 + 0], st);
-      a.d_x = cg->d_p; a.d_y = cg->d_tmp; a.init_sign = 1.0; a.post = B200_POST_DIV; a.d_d = cg->d_ry;
+      const bool re = cg->A_cg != nullptr && cg->At_cg != nullptr && cg->d_ry_cg != nullptr;
+      a.d_x = cg->d_p; a.d_y = cg->d_tmp; a.init_sign = 1.0; a.post = B200_POST_DIV;
+      a.d_d = re ? cg->d_ry_cg : cg->d_ry;
       a.d_skip = d_skip;
-      if (b200_spmv(cg->A, &a) != 0) ok = false;
+      if (b200_spmv(re ? cg->A_cg : cg->A, &a) != 0) ok = false;
       cudaEventRecord(ev[(size_t)r * 5 + 1], st);
       a.d_x = cg->d_tmp; a.d_y = cg->d_Gp; a.post = B200_POST_FMA_DOT; a.d_d = cg->d_rx; a.d_v = cg->d_p;
       a.d_dot = &cg->d_ctl->pGp; a.hook = B200_HOOK_CG_ALPHA; a.d_hook_arg = cg->d_ctl;
-      if (b200_spmv(cg->At, &a) != 0) ok = false;
+      if (b200_spmv(re ? cg->At_cg : cg->At, &a) != 0) ok = false;
       cudaEventRecord(ev[(size_t)r * 5 + 2], st);
       k_cg_update<<<g, VEC_THREADS, 0, st>>>(n, d_x, cg->d_r, cg->d_p, cg->d_Gp, cg->d_M, cg->d_z, cg->d_ctl,
                                              cg->d_partials, cg->d_counter);

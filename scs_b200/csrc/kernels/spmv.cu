@@ -62,6 +62,7 @@ struct B200Spmv {
   int nvrows;        // virtual rows (== nrows when no row was cut)
   int *d_vptr;       // nrows+1, or NULL
   double *d_vscratch;  // nvrows partial sums
+  int borrows;       // 1: d_rowptr / d_vals / d_wt3 / d_cta_begin3 belong to another operator (renumbered-columns view)
 };
 
 // random 8-byte gather of the dense vector: read-only path, optionally without L1 allocation
@@ -739,6 +740,47 @@ struct Spmv3Plan {
   int nvrows = 0;
 };
 
+// warp-tiles (whole (virtual) rows whose aligned span (k0 & ~3 .. end) is <= 128 entries) and the static CTA
+// partition, from the stored (virtual) row pointers alone -- shared by the host plan builder and the device one
+static void spmv3_tiles_from_rowptr(int nv, const int *vrp, long long stored, int grid_cap, Spmv3Plan &P) {
+  std::vector<int4> real;
+  real.reserve((size_t)(stored / 100 + 16));
+  for (int r = 0; r < nv;) {
+    const int k0 = vrp[r], base = k0 & ~3;
+    int r1 = r;
+    while (r1 < nv && vrp[r1 + 1] - base <= SPMV3_WT) ++r1;
+    int4 t;
+    t.x = r;
+    t.y = k0;
+    t.z = vrp[r1] - k0;
+    t.w = r1 - r;
+    real.push_back(t);
+    r = r1;
+  }
+  P.nwt = (int)real.size();
+  int grid = grid_cap < P.nwt ? grid_cap : P.nwt;
+  if (grid < 1) grid = 1;
+  P.grid = grid;
+  P.cta_begin.assign((size_t)grid + 1, 0);
+  P.wt.clear();
+  P.wt.reserve(real.size() + (size_t)grid * SPMV3_NCW);
+  for (int c = 0; c < grid; ++c) {
+    const long long a = (long long)P.nwt * c / grid, b = (long long)P.nwt * (c + 1) / grid;
+    for (long long w = a; w < b; ++w) P.wt.push_back(real[(size_t)w]);
+    // pad the CTA's list to whole groups with empty descriptors that continue the entry range
+    const int4 last = real[(size_t)(b - 1)];
+    while (P.wt.size() % SPMV3_NCW != 0) {
+      int4 t;
+      t.x = last.x + last.w;
+      t.y = last.y + last.z;
+      t.z = 0;
+      t.w = 0;
+      P.wt.push_back(t);
+    }
+    P.cta_begin[(size_t)c + 1] = (int)(P.wt.size() / SPMV3_NCW);
+  }
+}
+
 static bool spmv3_build_plan(int nrows, int ncols, const int *rp, const int *ci, const double *va,
                              int grid_cap, Spmv3Plan &P, bool split_long = false) {
   if (nrows <= 0 || ncols >= (1 << 30)) return false;
@@ -854,43 +896,7 @@ static bool spmv3_build_plan(int nrows, int ncols, const int *rp, const int *ci,
     vrp = vrp_store.data();
     P.nvrows = nv;
   }
-  // warp-tiles: whole (virtual) rows, aligned span (k0 & ~3 .. end) <= 128 entries
-  std::vector<int4> real;
-  real.reserve((size_t)(stored / 100 + 16));
-  for (int r = 0; r < nv;) {
-    const int k0 = vrp[r], base = k0 & ~3;
-    int r1 = r;
-    while (r1 < nv && vrp[r1 + 1] - base <= SPMV3_WT) ++r1;
-    int4 t;
-    t.x = r;
-    t.y = k0;
-    t.z = vrp[r1] - k0;
-    t.w = r1 - r;
-    real.push_back(t);
-    r = r1;
-  }
-  P.nwt = (int)real.size();
-  int grid = grid_cap < P.nwt ? grid_cap : P.nwt;
-  if (grid < 1) grid = 1;
-  P.grid = grid;
-  P.cta_begin.assign((size_t)grid + 1, 0);
-  P.wt.clear();
-  P.wt.reserve(real.size() + (size_t)grid * SPMV3_NCW);
-  for (int c = 0; c < grid; ++c) {
-    const long long a = (long long)P.nwt * c / grid, b = (long long)P.nwt * (c + 1) / grid;
-    for (long long w = a; w < b; ++w) P.wt.push_back(real[(size_t)w]);
-    // pad the CTA's list to whole groups with empty descriptors that continue the entry range
-    const int4 last = real[(size_t)(b - 1)];
-    while (P.wt.size() % SPMV3_NCW != 0) {
-      int4 t;
-      t.x = last.x + last.w;
-      t.y = last.y + last.z;
-      t.z = 0;
-      t.w = 0;
-      P.wt.push_back(t);
-    }
-    P.cta_begin[(size_t)c + 1] = (int)(P.wt.size() / SPMV3_NCW);
-  }
+  spmv3_tiles_from_rowptr(nv, vrp, stored, grid_cap, P);
   return true;
 }
 
@@ -1174,8 +1180,253 @@ extern "C" B200Spmv *b200_spmv_create(int nrows, int ncols, const int *h_rowptr,
   return M;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Device-side construction of a flagged-stream operator from a CSR that is ALREADY IN HBM (setup path of
+// scs_init_lin_sys_work, kernels/setup.cu): stored row pointers (every row >= 1 entry) by a scan, the flagged
+// stream by one fill kernel; only the row pointers travel back to the host for the (sequential, O(rows)) warp-tile
+// pass. Returns NULL when the operator needs what only the host builder offers (rows longer than a warp-tile,
+// forced v2, dimension limits) -- the caller then takes the host path.
+__global__ void k_stored_len(int nrows, const int *__restrict__ rp, int *__restrict__ out, int *maxlen) {
+  int mx = 0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+    const int len = rp[r + 1] - rp[r];
+    out[r] = len > 0 ? len : 1;
+    mx = len > mx ? len : mx;
+  }
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(maxlen, mx);
+}
+__global__ void k_fill_flagged(int nrows, const int *__restrict__ rp, const int *__restrict__ sp,
+                               const int *__restrict__ ci, const double *__restrict__ va, int *__restrict__ oi,
+                               double *__restrict__ ov) {
+  // one warp per row group: rows are short (<= SPMV3_MAXROW); lane-strided copy of each row
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r0 = warp * 32; r0 < nrows; r0 += nwarps * 32) {
+    const int r = r0 + lane;
+    if (r < nrows) {
+      const int a = rp[r], b = rp[r + 1];
+      int pos = sp[r];
+      if (a == b) {
+        oi[pos] = (int)(SPMV3_END | SPMV3_SKIP);
+        ov[pos] = 0.0;
+      } else {
+        for (int k = a; k < b; ++k, ++pos) {
+          oi[pos] = (k == b - 1) ? (int)((unsigned)ci[k] | SPMV3_END) : ci[k];
+          ov[pos] = va[k];
+        }
+      }
+    }
+  }
+}
+extern "C" int b200_dev_exclusive_scan_int(const int *d_in, int *d_out, int count);  // kernels/setup.cu (CUB)
+
+extern "C" B200Spmv *b200_spmv_create_dev(int nrows, int ncols, long long nnz, const int *d_rp, const int *d_ci,
+                                          const double *d_va) {
+  if (b200_runtime_init() != 0) return nullptr;
+  if (ncols >= (1 << 30) || nrows >= (1 << 30) || nrows <= 0) return nullptr;
+  {
+    const char *e = getenv("SCS_B200_SPMV");
+    if (e && atoi(e) == 2) return nullptr;
+    if (getenv("SCS_B200_SPMV_MINAVG")) return nullptr;
+  }
+  cudaStream_t st = (cudaStream_t)b200_stream();
+  B200Spmv *M = (B200Spmv *)calloc(1, sizeof(B200Spmv));
+  if (!M) return nullptr;
+  M->nrows = nrows; M->ncols = ncols; M->nnz = nnz; M->version = 3;
+  int *d_len = (int *)b200_malloc((size_t)(nrows + 1) * 4);
+  int *d_max = (int *)b200_malloc(4);
+  M->d_rowptr = (int *)b200_malloc((size_t)(nrows + 1 + 8) * 4);
+  std::vector<int> h_sp;
+  int h_max = 0, stored = 0;
+  Spmv3Plan P;
+  bool ok = d_len && d_max && M->d_rowptr;
+  if (ok) {
+    ok = b200_memset0(d_max, 4) == 0 && b200_memset0(M->d_rowptr, (size_t)(nrows + 1 + 8) * 4) == 0 &&
+         b200_memset0(d_len + nrows, 4) == 0;
+    int g = (nrows + 255) / 256;
+    if (g > 8 * b200_num_sms()) g = 8 * b200_num_sms();
+    if (ok) k_stored_len<<<g, 256, 0, st>>>(nrows, d_rp, d_len, d_max);
+    // exclusive scan over nrows + 1 items: element nrows receives the total
+    ok = ok && b200_dev_exclusive_scan_int(d_len, M->d_rowptr, nrows + 1) == 0;
+    ok = ok && b200_d2h(&h_max, d_max, 4) == 0;
+    h_sp.resize((size_t)nrows + 1);
+    ok = ok && b200_d2h(h_sp.data(), M->d_rowptr, (size_t)(nrows + 1) * 4) == 0 && b200_sync() == 0;
+    b200_count_launch(2);
+  }
+  if (ok && h_max > SPMV3_MAXROW) ok = false;  // virtual rows: host builder
+  if (ok) {
+    stored = h_sp[(size_t)nrows];
+    if (stored < 0) ok = false;
+  }
+  if (ok) {
+    const size_t pad = (((size_t)stored + 3) & ~(size_t)3) + 8;
+    M->stored = stored;
+    M->d_colidx = (int *)b200_malloc(pad * 4);
+    M->d_vals = (double *)b200_malloc(pad * 8);
+    ok = M->d_colidx && M->d_vals && b200_memset0(M->d_colidx, pad * 4) == 0 && b200_memset0(M->d_vals, pad * 8) == 0;
+    if (ok) {
+      int g = (nrows + 255) / 256;
+      if (g > 16 * b200_num_sms()) g = 16 * b200_num_sms();
+      k_fill_flagged<<<g, 256, 0, st>>>(nrows, d_rp, M->d_rowptr, d_ci, d_va, M->d_colidx, M->d_vals);
+      b200_count_launch(1);
+    }
+  }
+  if (ok) {
+    int cap = SPMV3_CTAS_PER_SM * b200_num_sms();
+    const char *gq = getenv("SCS_B200_SPMV_GRID");
+    if (gq && atoi(gq) > 0 && atoi(gq) < cap) cap = atoi(gq);
+    P.nvrows = nrows;
+    spmv3_tiles_from_rowptr(nrows, h_sp.data(), stored, cap, P);  // overlaps the fill kernel
+    M->grid = P.grid; M->ntiles = P.nwt; M->tile_nnz = SPMV3_WT; M->nvrows = nrows;
+    M->d_wt3 = (int4 *)b200_malloc(P.wt.size() * sizeof(int4));
+    M->d_cta_begin3 = (int *)b200_malloc(P.cta_begin.size() * 4);
+    M->d_partials = (double *)b200_malloc((size_t)B200_MAX_PARTIALS * 8);
+    M->d_counter = (unsigned int *)b200_malloc(64);
+    ok = M->d_wt3 && M->d_cta_begin3 && M->d_partials && M->d_counter && b200_memset0(M->d_counter, 64) == 0 &&
+         b200_h2d(M->d_wt3, P.wt.data(), P.wt.size() * sizeof(int4)) == 0 &&
+         b200_h2d(M->d_cta_begin3, P.cta_begin.data(), P.cta_begin.size() * 4) == 0 && b200_sync() == 0 &&
+         cudaGetLastError() == cudaSuccess;
+  }
+  b200_free(d_len);
+  b200_free(d_max);
+  if (!ok) {
+    b200_spmv_destroy(M);
+    return nullptr;
+  }
+  spmv_set_attrs();
+  return M;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reordered copies for the CG operator (measurements: profiles/README.md "reordering").
+// The m-space ordering INSIDE G = R_x + A' R_y^-1 A is free (tmp = R_y^-1 A p never leaves the operator), so the rows
+// of A can be sorted by their smallest column index: one gather per row of K1 becomes sequential, and the matching
+// entries of every column of A' become adjacent for K2.
+//   b200_spmv_permuted_rows : row-permuted copy of a flagged-stream operator (row `new` = row perm[new] of M);
+//                             segments are copied with their flags, the warp-tiles are recomputed;
+//   b200_spmv_refresh_permuted : values only (after the resident operators were rescaled in place);
+//   b200_spmv_renumbered_cols  : a VIEW of M whose stored column indices are mapped through inv[] (flags kept);
+//                             row pointers, values and warp-tiles are M's own (borrowed, not copied).
+__global__ void k_perm_len(int nrows, const int *__restrict__ sp, const int *__restrict__ perm, int *__restrict__ out) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+    const int o = perm[r];
+    out[r] = sp[o + 1] - sp[o];
+  }
+}
+__global__ void k_perm_copy(int nrows, const int *__restrict__ sp_old, const int *__restrict__ sp_new,
+                            const int *__restrict__ perm, const int *__restrict__ ci, const double *__restrict__ va,
+                            int *__restrict__ oi, double *__restrict__ ov) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
+    const int o = perm[r];
+    const int a = sp_old[o], len = sp_old[o + 1] - a;
+    const int b = sp_new[r];
+    for (int k = 0; k < len; ++k) {
+      if (oi != nullptr) oi[b + k] = ci[a + k];
+      ov[b + k] = va[a + k];
+    }
+  }
+}
+__global__ void k_renumber_cols(long long stored, const int *__restrict__ ci, const int *__restrict__ inv,
+                                int *__restrict__ out) {
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < stored; k += (long long)gridDim.x * blockDim.x) {
+    const unsigned v = (unsigned)ci[k];
+    out[k] = (v & SPMV3_SKIP) ? (int)v : (int)((unsigned)inv[v & 0x3fffffffu] | (v & SPMV3_END));
+  }
+}
+
+extern "C" B200Spmv *b200_spmv_permuted_rows(const B200Spmv *S, const int *d_perm) {
+  if (!S || S->version != 3 || S->d_vptr != nullptr) return nullptr;
+  cudaStream_t st = (cudaStream_t)b200_stream();
+  const int nrows = S->nrows;
+  B200Spmv *M = (B200Spmv *)calloc(1, sizeof(B200Spmv));
+  if (!M) return nullptr;
+  M->nrows = nrows; M->ncols = S->ncols; M->nnz = S->nnz; M->version = 3; M->stored = S->stored; M->nvrows = nrows;
+  const size_t pad = (((size_t)S->stored + 3) & ~(size_t)3) + 8;
+  int *d_len = (int *)b200_malloc((size_t)(nrows + 1) * 4);
+  M->d_rowptr = (int *)b200_malloc((size_t)(nrows + 1 + 8) * 4);
+  M->d_colidx = (int *)b200_malloc(pad * 4);
+  M->d_vals = (double *)b200_malloc(pad * 8);
+  M->d_partials = (double *)b200_malloc((size_t)B200_MAX_PARTIALS * 8);
+  M->d_counter = (unsigned int *)b200_malloc(64);
+  std::vector<int> h_sp((size_t)nrows + 1);
+  Spmv3Plan P;
+  int g = (nrows + 255) / 256;
+  if (g > 16 * b200_num_sms()) g = 16 * b200_num_sms();
+  bool ok = d_len && M->d_rowptr && M->d_colidx && M->d_vals && M->d_partials && M->d_counter;
+  ok = ok && b200_memset0(d_len + nrows, 4) == 0 && b200_memset0(M->d_rowptr, (size_t)(nrows + 1 + 8) * 4) == 0 &&
+       b200_memset0(M->d_colidx, pad * 4) == 0 && b200_memset0(M->d_vals, pad * 8) == 0 &&
+       b200_memset0(M->d_counter, 64) == 0;
+  if (ok) {
+    k_perm_len<<<g, 256, 0, st>>>(nrows, S->d_rowptr, d_perm, d_len);
+    ok = b200_dev_exclusive_scan_int(d_len, M->d_rowptr, nrows + 1) == 0;
+  }
+  if (ok) {
+    k_perm_copy<<<g, 256, 0, st>>>(nrows, S->d_rowptr, M->d_rowptr, d_perm, S->d_colidx, S->d_vals, M->d_colidx,
+                                   M->d_vals);
+    b200_count_launch(2);
+    ok = b200_d2h(h_sp.data(), M->d_rowptr, (size_t)(nrows + 1) * 4) == 0 && b200_sync() == 0;
+  }
+  if (ok) {
+    P.nvrows = nrows;
+    spmv3_tiles_from_rowptr(nrows, h_sp.data(), S->stored, S->grid > 0 ? SPMV3_CTAS_PER_SM * b200_num_sms() : 1, P);
+    M->grid = P.grid; M->ntiles = P.nwt; M->tile_nnz = SPMV3_WT;
+    M->d_wt3 = (int4 *)b200_malloc(P.wt.size() * sizeof(int4));
+    M->d_cta_begin3 = (int *)b200_malloc(P.cta_begin.size() * 4);
+    ok = M->d_wt3 && M->d_cta_begin3 && b200_h2d(M->d_wt3, P.wt.data(), P.wt.size() * sizeof(int4)) == 0 &&
+         b200_h2d(M->d_cta_begin3, P.cta_begin.data(), P.cta_begin.size() * 4) == 0 && b200_sync() == 0 &&
+         cudaGetLastError() == cudaSuccess;
+  }
+  b200_free(d_len);
+  if (!ok) {
+    b200_spmv_destroy(M);
+    return nullptr;
+  }
+  return M;
+}
+extern "C" int b200_spmv_refresh_permuted(B200Spmv *M, const B200Spmv *S, const int *d_perm) {
+  cudaStream_t st = (cudaStream_t)b200_stream();
+  int g = (M->nrows + 255) / 256;
+  if (g > 16 * b200_num_sms()) g = 16 * b200_num_sms();
+  k_perm_copy<<<g, 256, 0, st>>>(M->nrows, S->d_rowptr, M->d_rowptr, d_perm, nullptr, S->d_vals, nullptr, M->d_vals);
+  b200_count_launch(1);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+extern "C" B200Spmv *b200_spmv_renumbered_cols(const B200Spmv *S, const int *d_inv) {
+  if (!S || S->version != 3 || S->d_vptr != nullptr) return nullptr;
+  cudaStream_t st = (cudaStream_t)b200_stream();
+  B200Spmv *M = (B200Spmv *)calloc(1, sizeof(B200Spmv));
+  if (!M) return nullptr;
+  *M = *S;
+  M->borrows = 1;
+  const size_t pad = (((size_t)S->stored + 3) & ~(size_t)3) + 8;
+  M->d_colidx = (int *)b200_malloc(pad * 4);
+  M->d_partials = (double *)b200_malloc((size_t)B200_MAX_PARTIALS * 8);
+  M->d_counter = (unsigned int *)b200_malloc(64);
+  bool ok = M->d_colidx && M->d_partials && M->d_counter && b200_memset0(M->d_colidx, pad * 4) == 0 &&
+            b200_memset0(M->d_counter, 64) == 0;
+  if (ok) {
+    k_renumber_cols<<<8 * b200_num_sms(), 256, 0, st>>>(S->stored, S->d_colidx, d_inv, M->d_colidx);
+    b200_count_launch(1);
+    ok = cudaGetLastError() == cudaSuccess && b200_sync() == 0;
+  }
+  if (!ok) {
+    b200_spmv_destroy(M);
+    return nullptr;
+  }
+  return M;
+}
+
 extern "C" void b200_spmv_destroy(B200Spmv *M) {
   if (!M) return;
+  if (M->borrows) {  // a view: only the column indices, the reduction slots and the ticket counter are its own
+    b200_free(M->d_colidx);
+    b200_free(M->d_partials);
+    b200_free(M->d_counter);
+    free(M);
+    return;
+  }
   b200_free(M->d_rowptr);
   b200_free(M->d_colidx);
   b200_free(M->d_vals);

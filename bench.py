@@ -22,8 +22,8 @@ eps = 0 (so exactly K iterations run) -- identical algorithmic work, identical `
   roofline: the kernels of the CG loop AS THEY RUN IN THE SOLVE (spmv_flag_kernel<POST_DIV> on the solver's own p,
            <POST_FMA_DOT>+alpha hook on its tmp, k_cg_update, k_cg_pupdate), each bracketed by CUDA events inside
            genuine CG iterations; consecutive kernels stream 2 x 124 MB of matrix data, more than the 126 MB L2.
-  parity : the gates of SURVEY 8(d) measured in this very run: our first 3 ADMM iterations against the reference's
-           (the cpu_baseline sample), relative differences of x, y, s and the ScsInfo residuals.
+  parity : the gate of SURVEY 8(d) measured in this very run: our first ADMM iteration against the reference's
+           (run beside the cpu_baseline sample), relative differences of x, y, s and the ScsInfo residuals.
   cpu_baseline: the UNMODIFIED reference CPU-indirect solver (oracle/_ref, OpenMP build) on a bounded sample (the
            first 3 iterations) of the same workload.
 
@@ -161,13 +161,22 @@ def _reference_worker():
     t0 = time.time()
     w = ref.scs_init(C.byref(hp.data), C.byref(hp.cone), C.byref(st))
     t_init = time.time() - t0
+    if spec.get("dump"):
+        # parity sample for bench.py's "parity" gate: the FIRST iteration of a cold solve (the only window two correct
+        # implementations reproduce sharply, tests/test_reference_reproducibility_cpu.py); untimed
+        st1 = capi.default_settings(ref, verbose=0, max_iters=1, eps_abs=0.0, eps_rel=0.0, eps_infeas=0.0)
+        w1 = ref.scs_init(C.byref(hp.data), C.byref(hp.cone), C.byref(st1))
+        x1, y1, s1 = np.zeros(hp.n), np.zeros(hp.m), np.zeros(hp.m)
+        sol1 = capi.ScsSolution(capi.dptr(x1), capi.dptr(y1), capi.dptr(s1))
+        info1 = capi.ScsInfo()
+        ref.scs_solve(w1, C.byref(sol1), C.byref(info1), 0)
+        ref.scs_finish(w1)
+        np.savez(spec["dump"], x=x1, y=y1, s=s1, info=np.array([info1.pobj, info1.dobj, info1.res_pri, info1.res_dual,
+                                                                 info1.gap]))
     t0 = time.time()
     ref.scs_solve(w, C.byref(sol), C.byref(info), 0)
     t_solve = time.time() - t0
     ref.scs_finish(w)
-    if spec.get("dump"):
-        np.savez(spec["dump"], x=x, y=y, s=s, info=np.array([info.pobj, info.dobj, info.res_pri, info.res_dual,
-                                                               info.gap]))
     print("REFRESULT " + json.dumps({
         "iters": int(info.iter), "solve_s": t_solve, "init_s": t_init, "its_per_s": info.iter / t_solve,
         "e2e_its_per_s": info.iter / (t_solve + t_init), "lin_sys_ms": info.lin_sys_time,
@@ -457,15 +466,22 @@ def main():
                     # parity gate of SURVEY 8(d), measured in this run: our first k iterations vs the reference's
                     if os.path.exists(dump):
                         g = np.load(dump)
-                        wq, iq, sq = run_solver(lib, capi, hp, dict(max_iters=int(r["iters"]), **eps0))
+                        wq, iq, sq = run_solver(lib, capi, hp, dict(max_iters=1, **eps0))
                         lib.scs_finish(wq)
                         mine = [iq.pobj, iq.dobj, iq.res_pri, iq.res_dual, iq.gap]
-                        parity = {"window": f"first {r['iters']} ADMM iterations, cold start, vs the reference run of "
-                                            "cpu_baseline (max-norm relative differences; iterations >= 2 solve the "
-                                            "KKT system only to the adaptive CG tolerance)",
+                        parity = {"window": "the first ADMM iteration of a cold solve (equilibration, KKT solve at tol "
+                                            "1e-12, cone projection, un-normalisation) vs the unmodified reference run "
+                                            "on this host, max-norm relative differences; later iterations solve the "
+                                            "KKT system only to 0.2 x the residual and are not reproducible even "
+                                            "between the reference's own two builds "
+                                            "(tests/test_reference_reproducibility_cpu.py)",
+                                  "gate": "<= 1e-9 (north star 1e-10; the reference's own build-to-build spread is "
+                                          "1e-11 .. 1.5e-10)",
                                   "x": rel_err(sq[0], g["x"]), "y": rel_err(sq[1], g["y"]), "s": rel_err(sq[2], g["s"])}
                         for nm, a, b in zip(("pobj", "dobj", "res_pri", "res_dual", "gap"), mine, g["info"]):
                             parity[nm] = abs(a - b) / max(1.0, abs(b))
+                        parity["pass"] = bool(max(parity[k] for k in ("x", "y", "s", "pobj", "dobj", "res_pri",
+                                                                         "res_dual", "gap")) <= 1e-9)
                         os.remove(dump)
             except Exception as e:  # the checker must never break the measurement
                 cpu_base = {"value": None, "unit": "iters/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}

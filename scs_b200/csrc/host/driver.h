@@ -1,6 +1,7 @@
 /* driver.h -- private workspace of the device-resident ADMM driver
  * (counterpart of reference include/scs_work.h:55-86, with the iterate vectors
  * living in HBM instead of host memory). */
+#include <stdio.h>
 #ifndef B200_DRIVER_H
 #define B200_DRIVER_H
 #include "../../../include/scs_b200.h"
@@ -75,6 +76,10 @@ struct SCS_WORK {
   int rejected_accel_steps, accepted_accel_steps;
   /* stats of the last solve */
   long long stat_cg_iters, stat_solves, stat_launches;
+  /* per-iteration CSV trace (ScsSettings.log_csv_filename, reference src/rw.c:707-861): debugging mode, the
+   * iterates are copied to the host every iteration and every column is recomputed there */
+  FILE *log_csv_fout;
+  double *log_host; /* scratch: u, u_t, v, v_prev, rsk (l each), ax (m), aty (n), px (n) */
 };
 
 int b200_equilibrate(ScsMatrix *P, ScsMatrix *A, const int *bnd, int nbnd, double *D, double *E);

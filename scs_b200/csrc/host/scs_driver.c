@@ -223,6 +223,8 @@ static void *dup_mem(const void *src, size_t bytes) {
 void scs_finish(ScsWork *w) {
   if (!w) return;
   b200_sync();
+  if (w->log_csv_fout) fclose(w->log_csv_fout);
+  free(w->log_host);
   if (w->cones) b200_cones_destroy(w->cones);
   if (w->p) scs_free_lin_sys_work(w->p);
   if (w->accel) b200_aa_destroy(w->accel);
@@ -357,7 +359,6 @@ ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {
     printf("Writing raw problem data to %s\n", stgs->write_data_filename);
     scs_b200_write_data(stgs->write_data_filename, d, k, stgs);
   }
-  if (stgs->log_csv_filename) printf("WARN: log_csv_filename is not supported by scs_b200; ignored\n");
   w = (ScsWork *)calloc(1, sizeof(ScsWork));
   if (!w) return SCS_NULL;
   n = w->n = d->n;
@@ -395,6 +396,14 @@ ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {
   *w->stgs = *stgs;
   w->stgs->write_data_filename = SCS_NULL;
   w->stgs->log_csv_filename = SCS_NULL;
+  if (stgs->log_csv_filename) { /* reference scs.c:1275-1281 */
+    printf("Logging run data to %s\n", stgs->log_csv_filename);
+    w->log_csv_fout = fopen(stgs->log_csv_filename, "a");
+    if (!w->log_csv_fout) {
+      printf("Error: Could not open %s for writing\n", stgs->log_csv_filename);
+      goto fail;
+    }
+  }
   if (w->stgs->verbose) print_header(w);
 
   w->b_orig = (double *)malloc((size_t)m * 8);
@@ -876,6 +885,142 @@ static void print_summary(ScsWork *w, int i, double t0) {
   fflush(stdout);
 }
 
+/* ----------------------------------------------------------------- CSV trace
+ * One row per ADMM iteration, the columns of the reference's log_data_to_csv (src/rw.c:707-861) in the same order and
+ * format (%.16e), so that two traces can be diffed column by column. A debugging mode: the iterates and the residual
+ * vectors are copied to the host every iteration and every norm is recomputed there with the reference's formulas
+ * (populate_residual_struct / unnormalize_residuals, src/scs.c:487-607). As in the reference, logging refreshes the
+ * residual struct EVERY iteration, which feeds the CG tolerance of the next one (scs.c:1448-1453). */
+static double h_ninf(const double *v, long long len) {
+  double mx = 0.;
+  long long i;
+  for (i = 0; i < len; ++i) { const double a = fabs(v[i]); if (a > mx) mx = a; }
+  return mx;
+}
+static double h_n2(const double *v, long long len) {
+  double s = 0.;
+  long long i;
+  for (i = 0; i < len; ++i) s += v[i] * v[i];
+  return sqrt(s);
+}
+static int log_data_to_csv(ScsWork *w, int iter, double t_solve) {
+  const int n = w->n, m = w->m;
+  const long long l = (long long)n + m + 1;
+  const B200Residuals *r = &w->r_orig;
+  B200Residuals rn_local, *rn = &rn_local;
+  FILE *f = w->log_csv_fout;
+  double *u, *ut, *v, *vp, *rsk, *ax, *aty, *px;
+  double acc[16];
+  double tau, inv_ds, inv_ps;
+  long long i;
+  if (!f) return 0;
+  if (populate_residual_struct(w, iter) != 0) return -1;
+  if (!w->log_host) {
+    w->log_host = (double *)malloc((size_t)(5 * l + m + 2 * (long long)n) * sizeof(double));
+    if (!w->log_host) return -1;
+  }
+  u = w->log_host; ut = u + l; v = ut + l; vp = v + l; rsk = vp + l; ax = rsk + l; aty = ax + m; px = aty + n;
+  if (b200_d2h(u, w->adm.d_u, (size_t)l * 8) != 0 || b200_d2h(ut, w->adm.d_u_t, (size_t)l * 8) != 0 ||
+      b200_d2h(v, w->adm.d_v, (size_t)l * 8) != 0 || b200_d2h(vp, w->adm.d_v_prev, (size_t)l * 8) != 0 ||
+      b200_d2h(rsk, w->adm.d_rsk, (size_t)l * 8) != 0 || b200_d2h(ax, w->d_ax, (size_t)m * 8) != 0 ||
+      b200_d2h(aty, w->d_aty, (size_t)n * 8) != 0 || b200_sync() != 0)
+    return -1;
+  if (w->p->P) {
+    if (b200_d2h(px, w->d_px, (size_t)n * 8) != 0 || b200_sync() != 0) return -1;
+  } else {
+    memset(px, 0, (size_t)n * 8);
+  }
+  if (iter == 0) {
+    fprintf(f, "iter,res_pri,res_dual,gap,x_nrm_inf,y_nrm_inf,s_nrm_inf,x_nrm_2,y_nrm_2,s_nrm_2,"
+               "x_nrm_inf_normalized,y_nrm_inf_normalized,s_nrm_inf_normalized,x_nrm_2_normalized,y_nrm_2_normalized,"
+               "s_nrm_2_normalized,ax_s_btau_nrm_inf,px_aty_ctau_nrm_inf,ax_s_btau_nrm_2,px_aty_ctau_nrm_2,res_infeas,"
+               "res_unbdd_a,res_unbdd_p,pobj,dobj,tau,kap,res_pri_normalized,res_dual_normalized,gap_normalized,"
+               "ax_s_btau_nrm_inf_normalized,px_aty_ctau_nrm_inf_normalized,ax_s_btau_nrm_2_normalized,"
+               "px_aty_ctau_nrm_2_normalized,res_infeas_normalized,res_unbdd_a_normalized,res_unbdd_p_normalized,"
+               "pobj_normalized,dobj_normalized,tau_normalized,kap_normalized,ax_nrm_inf,ax_s_nrm_inf,px_nrm_inf,"
+               "aty_nrm_inf,xt_p_x,xt_p_x_tau,ctx,ctx_tau,bty,bty_tau,b_nrm_inf,c_nrm_inf,scale,diff_u_ut_nrm_2,"
+               "diff_v_v_prev_nrm_2,diff_u_ut_nrm_inf,diff_v_v_prev_nrm_inf,aa_norm,accepted_accel_steps,"
+               "rejected_accel_steps,time,spectral_Newton_iter,plain_Newton_success,res_dual_spectral,res_pri_spectral,"
+               "comp_spectral,\n");
+  }
+  tau = fabs(u[l - 1]);
+  inv_ds = 1.0 / w->dual_scale;
+  inv_ps = 1.0 / w->primal_scale;
+  /* the normalised residual struct with its infeasibility ratios (scs.c:598 compute_residuals(r, m, n, 1.0)): the
+   * device path keeps only what the iteration needs, the remaining normalised norms are taken from the host copies */
+  rn_local = w->r_norm;
+  rn_local.nm_aty = h_ninf(aty, n);
+  rn_local.nm_px = h_ninf(px, n);
+  {
+    double mx = 0.;
+    for (i = 0; i < m; ++i) { const double a = fabs(ax[i] + rsk[n + i]); if (a > mx) mx = a; }
+    rn_local.nm_ax_s = mx;
+  }
+  compute_residuals(&rn_local, 1.0);
+  /* acc: 0..5 inf/2-norms of x, y, s (original), 6..7 2-norms of ax_s_btau / px_aty_ctau (original),
+   * 8..9 the same normalised */
+  memset(acc, 0, sizeof(acc));
+  {
+    double xi = 0, x2 = 0, yi = 0, y2 = 0, si = 0, s2 = 0, p2 = 0, p2n = 0, d2 = 0, d2n = 0;
+    for (i = 0; i < n; ++i) {
+      const double e = w->E ? w->E[i] : 1.0;
+      const double xo = w->E ? u[i] * (e / w->dual_scale) : u[i];
+      const double rr = px[i] + aty[i] + tau * w->d->c[i];
+      const double ro = rr * (inv_ps / e);
+      if (fabs(xo) > xi) xi = fabs(xo);
+      x2 += xo * xo;
+      d2n += rr * rr;
+      d2 += ro * ro;
+    }
+    for (i = 0; i < m; ++i) {
+      const double d = w->D ? w->D[i] : 1.0;
+      const double yo = w->D ? u[n + i] * (d / w->primal_scale) : u[n + i];
+      const double so = w->D ? rsk[n + i] / (d * w->dual_scale) : rsk[n + i];
+      const double rr = ax[i] + rsk[n + i] - tau * w->d->b[i];
+      const double ro = rr * (inv_ds / d);
+      if (fabs(yo) > yi) yi = fabs(yo);
+      if (fabs(so) > si) si = fabs(so);
+      y2 += yo * yo;
+      s2 += so * so;
+      p2n += rr * rr;
+      p2 += ro * ro;
+    }
+    acc[0] = xi; acc[1] = yi; acc[2] = si; acc[3] = sqrt(x2); acc[4] = sqrt(y2); acc[5] = sqrt(s2);
+    acc[6] = sqrt(p2); acc[7] = sqrt(d2); acc[8] = sqrt(p2n); acc[9] = sqrt(d2n);
+  }
+  fprintf(f, "%li,", (long)iter);
+  fprintf(f, "%.16e,%.16e,%.16e,", r->res_pri, r->res_dual, r->gap);
+  fprintf(f, "%.16e,%.16e,%.16e,%.16e,%.16e,%.16e,", acc[0], acc[1], acc[2], acc[3], acc[4], acc[5]);
+  fprintf(f, "%.16e,%.16e,%.16e,", h_ninf(u, n), h_ninf(u + n, m), h_ninf(rsk + n, m));
+  fprintf(f, "%.16e,%.16e,%.16e,", h_n2(u, n), h_n2(u + n, m), h_n2(rsk + n, m));
+  fprintf(f, "%.16e,%.16e,%.16e,%.16e,", r->nm_ax_s_btau, r->nm_px_aty_ctau, acc[6], acc[7]);
+  fprintf(f, "%.16e,%.16e,%.16e,", r->res_infeas, r->res_unbdd_a, r->res_unbdd_p);
+  fprintf(f, "%.16e,%.16e,%.16e,%.16e,", r->pobj, r->dobj, r->tau, r->kap);
+  fprintf(f, "%.16e,%.16e,%.16e,", rn->res_pri, rn->res_dual, rn->gap);
+  fprintf(f, "%.16e,%.16e,%.16e,%.16e,", rn->nm_ax_s_btau, rn->nm_px_aty_ctau, acc[8], acc[9]);
+  fprintf(f, "%.16e,%.16e,%.16e,", rn->res_infeas, rn->res_unbdd_a, rn->res_unbdd_p);
+  fprintf(f, "%.16e,%.16e,%.16e,%.16e,", rn->pobj, rn->dobj, rn->tau, rn->kap);
+  fprintf(f, "%.16e,%.16e,%.16e,%.16e,", r->nm_ax, r->nm_ax_s, r->nm_px, r->nm_aty);
+  fprintf(f, "%.16e,%.16e,%.16e,%.16e,%.16e,%.16e,", r->xt_p_x, r->xt_p_x_tau, r->ctx, r->ctx_tau, r->bty, r->bty_tau);
+  fprintf(f, "%.16e,%.16e,%.16e,", w->nm_b_orig, w->nm_c_orig, w->stgs->scale);
+  {
+    double du2 = 0, dv2 = 0, dui = 0, dvi = 0;
+    for (i = 0; i < l; ++i) {
+      const double a = u[i] - ut[i], b = v[i] - vp[i];
+      du2 += a * a;
+      dv2 += b * b;
+      if (fabs(a) > dui) dui = fabs(a);
+      if (fabs(b) > dvi) dvi = fabs(b);
+    }
+    fprintf(f, "%.16e,%.16e,%.16e,%.16e,", sqrt(du2), sqrt(dv2), dui, dvi);
+  }
+  fprintf(f, "%.16e,%li,%li,", w->aa_norm, (long)w->accepted_accel_steps, (long)w->rejected_accel_steps);
+  fprintf(f, "%.16e,", (now_ms() - t_solve) / 1e3);
+  fprintf(f, "0,0,%.16e,%.16e,%.16e,", 0.0, 0.0, 0.0); /* spectral-cone Newton statistics: no spectral cones here */
+  fprintf(f, "\n");
+  return 0;
+}
+
 /* ----------------------------------------------------------------- the solve */
 scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_int warm_start) {
   int i, l;
@@ -976,7 +1121,12 @@ scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_int warm_star
       else w->accepted_accel_steps++;
       b200_section_mark(B200_SEC_ACCEL);
     }
+    /* log AFTER the scale update so that the residual recalculation does not affect the algorithm (scs.c:1448-1453) */
+    if (w->log_csv_fout && log_data_to_csv(w, i, t_solve) != 0)
+      return failure(w, w->m, w->n, sol, info, SCS_FAILED, "error in log_data_to_csv", "failure");
   }
+  if (w->log_csv_fout && log_data_to_csv(w, i, t_solve) != 0) /* final row after the full run (scs.c:1457-1461) */
+    return failure(w, w->m, w->n, sol, info, SCS_FAILED, "error in log_data_to_csv", "failure");
   b200_section_mark(B200_SEC_OTHER);
   if (b200_section_flush() != 0 || b200_cones_check(w->cones) != 0)
     return failure(w, w->m, w->n, sol, info, SCS_FAILED, "error in project_cones", "failure");

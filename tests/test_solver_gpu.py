@@ -297,6 +297,34 @@ def test_complex_psd_cone_matches_reference(lib, reflib):
     assert abs(info_m.pobj - opt) <= 1000 * eps * max(1.0, abs(opt))
 
 
+def test_csv_trace_matches_reference(lib, reflib, tmp_path):
+    """log_csv_filename (reference src/rw.c:707-861): same columns, same format; the row of iteration 0 -- everything
+    up to and including the first cone projection and residual computation -- agrees with the reference's to 1e-9;
+    later rows are compared loosely (CG at the adaptive tolerance, tests/test_reference_reproducibility_cpu.py)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import csv_trace_diff
+    prob = small_problem("socp", seed=4)
+    mine, ref = str(tmp_path / "mine.csv"), str(tmp_path / "ref.csv")
+    over = dict(max_iters=30, acceleration_lookback=0, eps_abs=1e-12, eps_rel=1e-12)
+    st_m, info_m, *_ = solve_with(lib, prob, log_csv_filename=mine.encode(), **over)
+    st_r, info_r, *_ = solve_with(reflib, prob, log_csv_filename=ref.encode(), **over)
+    assert st_m == st_r
+    hm, rm = csv_trace_diff.read(mine)
+    hr, rr = csv_trace_diff.read(ref)
+    assert hm[:62] == hr[:62]                       # identical column names, identical order
+    assert len(rm) == len(rr) == 31                 # one row per iteration + the final row
+    first, _ = csv_trace_diff.compare(mine, ref, nrows=1)
+    worst = max(v[0] for v in first.values())
+    print(f"\n[csv trace] iteration-0 row: worst relative difference {worst:.2e} over {len(first)} columns")
+    assert worst <= 1e-9, {k: v for k, v in first.items() if v[0] > 1e-9}
+    allrows, n = csv_trace_diff.compare(mine, ref)
+    print(f"[csv trace] all {n} rows: worst {max(v[0] for v in allrows.values()):.2e} "
+          f"(res_pri {allrows['res_pri'][0]:.1e}, pobj {allrows['pobj'][0]:.1e})")
+    assert allrows["iter"][0] == 0.0 and allrows["scale"][0] == 0.0
+
+
 def test_sigint_stops_a_long_solve(lib):
     """Ctrl-C contract of the reference (src/ctrlc.c, src/scs.c:1400-1403): SIGINT during scs_solve ends it with
     SCS_SIGINT (-5) / status "interrupted", NaN solution, and the previous handler is restored afterwards."""

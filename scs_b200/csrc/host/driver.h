@@ -78,7 +78,8 @@ struct SCS_WORK {
   long long stat_cg_iters, stat_solves, stat_launches;
   /* per-iteration CSV trace (ScsSettings.log_csv_filename, reference src/rw.c:707-861): debugging mode, the
    * iterates are copied to the host every iteration and every column is recomputed there */
-  FILE *log_csv_fout;
+  char *log_csv_name; /* deep copy of ScsSettings.log_csv_filename */
+  FILE *log_csv_fout; /* opened ("w") at the start of every scs_solve, closed at its end (rw.c:686-705) */
   double *log_host; /* scratch: u, u_t, v, v_prev, rsk (l each), ax (m), aty (n), px (n) */
 };
 

@@ -224,6 +224,7 @@ void scs_finish(ScsWork *w) {
   if (!w) return;
   b200_sync();
   if (w->log_csv_fout) fclose(w->log_csv_fout);
+  free(w->log_csv_name);
   free(w->log_host);
   if (w->cones) b200_cones_destroy(w->cones);
   if (w->p) scs_free_lin_sys_work(w->p);
@@ -396,13 +397,10 @@ ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {
   *w->stgs = *stgs;
   w->stgs->write_data_filename = SCS_NULL;
   w->stgs->log_csv_filename = SCS_NULL;
-  if (stgs->log_csv_filename) { /* reference scs.c:1275-1281 */
+  if (stgs->log_csv_filename) { /* reference scs.c:1275-1278; the file is opened by every scs_solve */
     printf("Logging run data to %s\n", stgs->log_csv_filename);
-    w->log_csv_fout = fopen(stgs->log_csv_filename, "a");
-    if (!w->log_csv_fout) {
-      printf("Error: Could not open %s for writing\n", stgs->log_csv_filename);
-      goto fail;
-    }
+    w->log_csv_name = (char *)dup_mem(stgs->log_csv_filename, strlen(stgs->log_csv_filename) + 1);
+    if (!w->log_csv_name) goto fail;
   }
   if (w->stgs->verbose) print_header(w);
 
@@ -1036,6 +1034,11 @@ scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_int warm_star
   stgs = w->stgs;
   stgs->warm_start = warm_start;
   t_solve = now_ms();
+  if (w->log_csv_name) { /* reference rw.c:686-698, scs.c:1349 */
+    if (w->log_csv_fout) fclose(w->log_csv_fout);
+    w->log_csv_fout = fopen(w->log_csv_name, "w");
+    if (!w->log_csv_fout) printf("Error: Could not open %s for writing\n", w->log_csv_name);
+  }
   start_interrupt_listener();
   strcpy(info->lin_sys_solver, scs_get_lin_sys_method());
   info->status_val = SCS_UNFINISHED;
@@ -1147,6 +1150,10 @@ scs_int scs_solve(ScsWork *w, ScsSolution *sol, ScsInfo *info, scs_int warm_star
   w->stat_cg_iters = w->p->tot_cg_its - cg0;
   w->stat_solves = w->p->n_solves - solves0;
   w->stat_launches = b200_launches() - launches0;
+  if (w->log_csv_fout) { /* scs.c:1481 */
+    fclose(w->log_csv_fout);
+    w->log_csv_fout = SCS_NULL;
+  }
   end_interrupt_listener();
   if (stgs->verbose) {
     int k;

@@ -268,8 +268,10 @@ static void setup_mark(const char *what, double *t_last) {
 /* The reordered pair used inside the CG operator (kernels/spmv.cu "Reordered copies"): built once, values and R_y
  * refreshed whenever the resident operators may have been rescaled (b200_linsys_update_diag_r_dev). */
 static int cg_ops_build(ScsLinSysWork *w) {
+  /* OFF by default: measured on C2 (profiles/README.md, round 2 call C) the reordered pair makes K2 1.6 us faster
+   * (62.1 -> 60.5 us) but K1 25 us SLOWER (64.9 -> 90.1 us); SCS_B200_REORDER=1 enables it for experiments */
   const char *e = getenv("SCS_B200_REORDER");
-  if (w->nranks > 1 || (e && atoi(e) == 0)) return 0;
+  if (w->nranks > 1 || !(e && atoi(e) != 0)) return 0;
   if (!b200_spmv_can_route(w->A) || !b200_spmv_can_route(w->At)) return 0; /* one-pass flagged streams only */
   w->d_perm = (int *)b200_malloc((size_t)w->m * 4);
   w->d_inv = (int *)b200_malloc((size_t)w->m * 4);

@@ -12,10 +12,26 @@
 #include "../dev_api.h"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <stdio.h>
 #include <stdlib.h>
 
 extern "C" B200Spmv *b200_spmv_create_dev(int nrows, int ncols, long long nnz, const int *d_rp, const int *d_ci,
                                           const double *d_va);
+
+#include <time.h>
+// SCS_B200_SETUP_TIMING=1: wall-clock marks inside the device builder (syncs at every mark)
+static double setup_now_ms() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+}
+static void dev_mark(const char *what, double *t_last) {
+  if (!getenv("SCS_B200_SETUP_TIMING")) return;
+  b200_sync();
+  const double t = setup_now_ms();
+  fprintf(stderr, "scs_b200 setup:     device builder: %-28s %8.1f ms\n", what, t - *t_last);
+  *t_last = t;
+}
 
 extern "C" int b200_dev_exclusive_scan_int(const int *d_in, int *d_out, int count) {
   cudaStream_t st = (cudaStream_t)b200_stream();
@@ -80,14 +96,18 @@ extern "C" int b200_setup_ops_from_csc(int m, int n, const int *h_Ap, const int 
   int rc = -1;
   B200Spmv *A = nullptr, *At = nullptr;
   const int nsm = b200_num_sms();
+  double t_mark = setup_now_ms();
+  dev_mark("allocations", &t_mark);
   do {
     if (!d_Ap || !d_Ai || !d_Ax || !d_Tp || !d_cnt || !d_Ti || !d_Tx || !d_cols || !d_iota || !d_keys || !d_perm) break;
     if (b200_h2d(d_Ap, h_Ap, (size_t)(n + 1) * 4) != 0 || b200_h2d(d_Ai, h_Ai, (size_t)nnz * 4) != 0 ||
         b200_h2d(d_Ax, h_Ax, (size_t)nnz * 8) != 0)
       break;
+    dev_mark("H2D of the CSC arrays", &t_mark);
     // A' first: its CSR is the CSC as given
     At = b200_spmv_create_dev(n, m, nnz, d_Ap, d_Ai, d_Ax);
     if (!At) { rc = 1; break; }
+    dev_mark("operator A' (stream + tiles)", &t_mark);
     // transpose: row counts -> row pointers; stable sort of (row, entry id) -> entries of each row by ascending column
     if (b200_memset0(d_cnt, (size_t)(m + 2) * 4) != 0) break;
     k_count_rows<<<8 * nsm, 256, 0, st>>>(nnz, d_Ai, d_cnt);
@@ -108,13 +128,16 @@ extern "C" int b200_setup_ops_from_csc(int m, int n, const int *h_Ap, const int 
     k_gather_transposed<<<8 * nsm, 256, 0, st>>>(nnz, d_perm, d_cols, d_Ax, d_Ti, d_Tx);
     b200_count_launch(4);
     if (cudaGetLastError() != cudaSuccess || b200_sync() != 0) break;
+    dev_mark("transpose (count, scan, sort)", &t_mark);
     A = b200_spmv_create_dev(m, n, nnz, d_Tp, d_Ti, d_Tx);
     if (!A) { rc = 1; break; }
+    dev_mark("operator A (stream + tiles)", &t_mark);
     rc = 0;
   } while (0);
   b200_sync();
   b200_free(d_Ap); b200_free(d_Ai); b200_free(d_Ax); b200_free(d_Tp); b200_free(d_cnt); b200_free(d_Ti);
   b200_free(d_Tx); b200_free(d_cols); b200_free(d_iota); b200_free(d_keys); b200_free(d_perm); b200_free(d_tmp);
+  dev_mark("frees", &t_mark);
   if (rc != 0) {
     b200_spmv_destroy(A);
     b200_spmv_destroy(At);

@@ -510,11 +510,14 @@ __device__ __forceinline__ double *px_scal(const P2pViewX &pv, int r, int round,
 }
 __device__ __forceinline__ void px_wait(volatile unsigned long long *line, int first, int G, int skip_rank,
                                         unsigned long long seq, B200CgCtl *ctl) {
+  // never hang the GPU: a wait gives up after ~1.5 s (3e9 cycles) and raises the error flag; once the flag is up every
+  // later wait of this and the following iterations returns at once (the host aborts the solve when it sees it)
+  if (*((volatile int *)&ctl->pad[0])) return;
   const long long t0 = clock64();
   for (int r = 0; r < G; ++r) {
     if (r == skip_rank) continue;
     while (line[first + r] < seq) {
-      if (clock64() - t0 > 20000000000LL) { ctl->pad[0] = 1; break; }  // ~10 s: never hang the GPU
+      if (clock64() - t0 > 3000000000LL) { ctl->pad[0] = 1; return; }
     }
   }
   __threadfence_system();
@@ -525,7 +528,7 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int y_has_px,
                 const double *__restrict__ rx, const double *__restrict__ M, double *p,
                 double *__restrict__ Gp, double *__restrict__ x, double *__restrict__ r,
                 double *__restrict__ z, B200CgCtl *ctl, double *partials, unsigned int *counters) {
-  if (ctl->done) return;
+  if (ctl->done || ctl->pad[0]) return;
   __shared__ double s_red[128];
   __shared__ double s_bc[4];
   const int G = pv.nranks, me = pv.rank;

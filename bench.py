@@ -19,7 +19,7 @@ eps = 0 (so exactly K iterations run) -- identical algorithmic work, identical `
   time_to_eps_1e-4 : the other half of BASELINE's metric -- a separate default-settings solve to eps_abs =
            eps_rel = 1e-4 (status, iterations, setup and solve seconds, residuals); the CPU reference needs hours
            for this, its figure is an extrapolation from its measured iterations/s and labelled so.
-  roofline: the kernels of the CG loop AS THEY RUN IN THE SOLVE (spmv_flag_kernel<POST_DIV> on the solver's own p,
+  roofline: the kernels of the CG loop AS THEY RUN IN THE SOLVE (spmv_flag_kernel<POST_MUL> on the solver's own p,
            <POST_FMA_DOT>+alpha hook on its tmp, k_cg_update, k_cg_pupdate), each bracketed by CUDA events inside
            genuine CG iterations; consecutive kernels stream 2 x 124 MB of matrix data, more than the 126 MB L2.
   parity : the gate of SURVEY 8(d) measured in this very run: our first ADMM iteration against the reference's
@@ -434,7 +434,7 @@ def main():
         rc = lib.scs_b200_time_cg_kernels(lw, capi.dptr(rhs), 50, ms, by)
         lib.scs_free_lin_sys_work(lw)
         if rc == 0:
-            names = ["K1 spmv_flag_kernel<POST_DIV>: tmp = R_y^-1 (A p)  [rows of A, gathers p]",
+            names = ["K1 spmv_flag_kernel<POST_MUL>: tmp = R_y^-1 (A p)  [rows of A, gathers p]",
                      "K2 spmv_flag_kernel<POST_FMA_DOT>+alpha hook: Gp = R_x p + A' tmp, p'Gp  [columns of A, gathers tmp]",
                      "K3 k_cg_update: x += a p, r -= a Gp, z = M r, z'r, |r|_inf, beta",
                      "K4 k_cg_pupdate: p = z + beta p",

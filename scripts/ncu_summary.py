@@ -54,11 +54,11 @@ def main():
             return v * (1e9 if u.startswith("g") else 1e6 if u.startswith("m") else 1e3 if u.startswith("k") else 1.0)
 
         tr = {}
-        # launches are classified by the kernel's template argument: spmv_flag_kernel<1> = K1 (POST_DIV, tmp = R_y^-1 A p),
+        # launches are classified by the kernel's template argument: spmv_flag_kernel<4> = K1 (POST_MUL, tmp = R_y^-1 A p; <1> = POST_DIV before round 2 call E),
         # <2> = K2 (POST_FMA_DOT + alpha hook, Gp = R_x p + A' tmp) -- the in-loop kernels of scripts/prof_cg.py;
         # <0> launches alternate A x (even) / A'x (odd) in scripts/prof_spmv.py
         name = col["Kernel Name"]
-        groups = {"K1": [r for r in data if "spmv_flag_kernel<1>" in r[name]],
+        groups = {"K1": [r for r in data if "spmv_flag_kernel<4>" in r[name] or "spmv_flag_kernel<1>" in r[name]],
                   "K2": [r for r in data if "spmv_flag_kernel<2>" in r[name]]}
         plain = [r for r in data if "spmv_flag_kernel<0>" in r[name]]
         groups["A x"], groups["A'x"] = plain[0::2], plain[1::2]

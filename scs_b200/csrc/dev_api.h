@@ -62,7 +62,10 @@ const int *b200_spmv_rowptr(const B200Spmv *M);    /* device */
 /* algorithmic bytes of one launch: 12 nnz + 4 (R+1) + 8 C + 8 R (+ 8 R per extra row vector) */
 double b200_spmv_alg_bytes(const B200Spmv *M, int extra_row_vectors);
 
-enum { B200_POST_NONE = 0, B200_POST_DIV = 1, B200_POST_FMA_DOT = 2, B200_POST_FMA = 3 };
+enum { B200_POST_NONE = 0, B200_POST_DIV = 1, B200_POST_FMA_DOT = 2, B200_POST_FMA = 3, B200_POST_MUL = 4 };
+/* B200_POST_MUL: y = s * d[r] with d = R_y^-1 precomputed -- what the reference's own GPU backend does
+ * (linsys/gpu/indirect/private.c:78,164: inv_r_y, scale_by_diag); used by K1 inside the CG loop, where the fp64
+ * division chain of POST_DIV held the warps out of the gather pipeline (profiles/README.md, round 2). */
 enum { B200_HOOK_NONE = 0, B200_HOOK_CG_ALPHA = 1, B200_HOOK_P2P_SIGNAL = 2, B200_HOOK_P2P_ROUTE = 3 };
 /* B200_HOOK_P2P_SIGNAL: when the LAST block of the launch has stored its rows, it publishes
  * hook_val into slot `rank` of every peer's flag line (d_hook_arg -> B200P2pSignal). */
@@ -88,7 +91,7 @@ typedef struct {
   double *d_y;           /* output, length nrows */
   const double *d_init;  /* NULL: chain starts at 0; else at init_sign * d_init[r] (may alias d_y) */
   double init_sign;
-  int post;              /* B200_POST_*: y = s | s / d[r] | fma(d[r], v[r], s) with dot(v, y) | same, no dot */
+  int post;              /* B200_POST_*: y = s | s / d[r] | fma(d[r], v[r], s) with dot(v, y) | same, no dot | s * d[r] */
   const double *d_d;
   const double *d_v;
   double *d_dot;         /* B200_POST_FMA_DOT: receives sum_r v[r]*y[r] */
@@ -136,6 +139,7 @@ typedef struct {
   const double *d_ry_cg;
   const double *d_rx;  /* R_x (n) */
   const double *d_ry;  /* R_y (m) */
+  double *d_ry_inv;    /* 1 / R_y (m), refreshed by b200_cg_set_preconditioner */
   double *d_M;         /* Jacobi preconditioner (n) */
   double *d_p, *d_r, *d_Gp, *d_z, *d_tmp; /* n, n, n, n, m */
   B200CgCtl *d_ctl;

@@ -287,7 +287,7 @@ static int cg_ops_build(ScsLinSysWork *w) {
 static int cg_ops_refresh(ScsLinSysWork *w) {
   if (!w->A_cg) return 0;
   if (b200_spmv_refresh_permuted(w->A_cg, w->A, w->d_perm) != 0) return -1;
-  return b200_gather_vec(w->m, w->d_perm, w->d_diag_r + w->n, w->d_ry_cg);
+  return b200_gather_vec(w->m, w->d_perm, w->cg.d_ry_inv, w->d_ry_cg); /* 1 / R_y in the permuted order */
 }
 
 ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
@@ -364,6 +364,7 @@ ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
   w->cg.d_Gp = (double *)b200_malloc((size_t)n * 8);
   w->cg.d_z = (double *)b200_malloc((size_t)n * 8);
   w->cg.d_tmp = (double *)b200_malloc((size_t)m * 8);
+  w->cg.d_ry_inv = (double *)b200_malloc((size_t)m * 8);
   w->cg.d_ctl = (B200CgCtl *)b200_malloc(sizeof(B200CgCtl));
   w->cg.d_partials = (double *)b200_malloc(4 * 2048 * 8);
   w->cg.d_counter = (unsigned int *)b200_malloc(64);
@@ -371,7 +372,7 @@ ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
   w->cg.h_ctl = (B200CgCtl *)b200_host_alloc(sizeof(B200CgCtl));
   if (!w->d_diag_r || !w->d_b || !w->d_s || !w->cg.d_M || !w->cg.d_r ||
       !w->cg.d_Gp || !w->cg.d_z || !w->cg.d_tmp || !w->cg.d_ctl || !w->cg.d_partials ||
-      !w->cg.d_counter || !w->cg.h_ctl || !w->cg.d_red)
+      !w->cg.d_counter || !w->cg.h_ctl || !w->cg.d_red || !w->cg.d_ry_inv)
     goto fail;
   b200_memset0(w->cg.d_counter, 64);
   b200_memset0(w->cg.d_ctl, sizeof(B200CgCtl));
@@ -448,6 +449,7 @@ void scs_free_lin_sys_work(ScsLinSysWork *w) {
   b200_free(w->cg.d_Gp);
   b200_free(w->cg.d_z);
   b200_free(w->cg.d_tmp);
+  b200_free(w->cg.d_ry_inv);
   b200_free(w->cg.d_ctl);
   b200_free(w->cg.d_partials);
   b200_free(w->cg.d_counter);
@@ -499,8 +501,8 @@ int b200_linsys_update_diag_r_dev(ScsLinSysWork *w, const double *d_diag_r) {
   if (d_diag_r != w->d_diag_r) {
     if (b200_d2d(w->d_diag_r, d_diag_r, ((size_t)w->n + w->m) * 8) != 0) return -1;
   }
-  if (cg_ops_refresh(w) != 0) return -1; /* the operators may have been rescaled in place; R_y has changed */
-  return b200_cg_set_preconditioner(&w->cg, w->d_Pdiag);
+  if (b200_cg_set_preconditioner(&w->cg, w->d_Pdiag) != 0) return -1; /* also refreshes 1 / R_y */
+  return cg_ops_refresh(w); /* the operators may have been rescaled in place; R_y has changed */
 }
 
 scs_int scs_solve_lin_sys(ScsLinSysWork *w, scs_float *b, const scs_float *s, scs_float tol) {

@@ -698,9 +698,16 @@ __global__ void k_precond_finish(int n, const double *__restrict__ rx, const dou
   }
 }
 
+__global__ void k_recip(long long len, const double *__restrict__ v, double *__restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x)
+    out[i] = 1.0 / v[i];
+}
 // ---------------------------------------------------------------------------
 extern "C" int b200_cg_set_preconditioner(const B200Cg *cg, const double *d_Pdiag) {
   cudaStream_t st = (cudaStream_t)b200_stream();
+  // R_y^-1 for K1 (reference linsys/gpu/indirect/private.c:75-80 keeps the same inverse)
+  k_recip<<<vec_grid(cg->m), 256, 0, st>>>(cg->m, cg->d_ry, cg->d_ry_inv);
+  b200_count_launch(1);
   if (cg->nranks > 1) {
     k_precond_partial<<<vec_grid(cg->n), 256, 0, st>>>(cg->n, b200_spmv_rowptr(cg->At),
                                                       b200_spmv_colidx(cg->At), b200_spmv_vals(cg->At),
@@ -741,8 +748,8 @@ static int mat_vec_sharded(B200Cg *cg, const double *d_x, double *d_y, int with_
   B200SpmvArgs a;
   memset(&a, 0, sizeof(a));
   // K1 (local rows): tmp[row0:row0+mloc] = (A_g x) ./ R_y
-  a.d_x = d_x; a.d_y = cg->d_tmp + cg->row0; a.init_sign = 1.0; a.post = B200_POST_DIV;
-  a.d_d = cg->d_ry + cg->row0; a.d_skip = d_skip;
+  a.d_x = d_x; a.d_y = cg->d_tmp + cg->row0; a.init_sign = 1.0; a.post = B200_POST_MUL;
+  a.d_d = cg->d_ry_inv + cg->row0; a.d_skip = d_skip;
   if (b200_spmv(cg->A, &a) != 0) return -1;
   // local partial  red = A_g' tmp_g ; sum over ranks
   unsigned long long seq = 0;
@@ -806,7 +813,7 @@ static int mat_vec(B200Cg *cg, const double *d_x, double *d_y, int with_dot, con
   // K1: tmp = (A x) ./ R_y
   a.pdl = cg_pdl_enabled() ? 1 : 0;
   a.d_x = d_x; a.d_y = cg->d_tmp; a.d_init = nullptr; a.init_sign = 1.0;
-  a.post = B200_POST_DIV; a.d_d = re ? cg->d_ry_cg : cg->d_ry; a.d_v = nullptr; a.d_dot = nullptr;
+  a.post = B200_POST_MUL; a.d_d = re ? cg->d_ry_cg : cg->d_ry_inv; a.d_v = nullptr; a.d_dot = nullptr;
   a.hook = B200_HOOK_NONE; a.d_hook_arg = nullptr; a.d_skip = d_skip;
   if (b200_spmv(A, &a) != 0) return -1;
   const double *init = nullptr;
@@ -843,8 +850,8 @@ static int cg_iteration_shard_x(B200Cg *cg, double *d_x) {
   B200SpmvArgs a;
   memset(&a, 0, sizeof(a));
   // K1 (local rows): tmp_g = (A_g p) ./ R_g
-  a.d_x = cg->d_p; a.d_y = cg->d_tmp + cg->row0; a.init_sign = 1.0; a.post = B200_POST_DIV;
-  a.d_d = cg->d_ry + cg->row0; a.d_skip = d_skip;
+  a.d_x = cg->d_p; a.d_y = cg->d_tmp + cg->row0; a.init_sign = 1.0; a.post = B200_POST_MUL;
+  a.d_d = cg->d_ry_inv + cg->row0; a.d_skip = d_skip;
   if (b200_spmv(cg->A, &a) != 0) return -1;
   // K2: partial A_g' tmp_g, every row pushed to its owner's inbox; the last block signals "partial ready"
   const unsigned long long seq = b200_p2p_next_seq();
@@ -899,7 +906,7 @@ extern "C" int b200_cg_one_iteration(B200Cg *cg, double *d_x) { return cg_iterat
 
 // Per-kernel device times of the CG loop AS IT RUNS IN A SOLVE (bench.py roofline): `reps` genuine iterations on
 // the solver's own p / tmp / r, every kernel bracketed by CUDA events on the library stream. out_ms[0..3] = average
-// per launch of K1 (tmp = R_y^-1 A p, spmv POST_DIV), K2 (Gp = R_x p + A' tmp, p'Gp, alpha: spmv POST_FMA_DOT + hook),
+// per launch of K1 (tmp = R_y^-1 A p, spmv POST_MUL), K2 (Gp = R_x p + A' tmp, p'Gp, alpha: spmv POST_FMA_DOT + hook),
 // K3 (k_cg_update), K4 (k_cg_pupdate); out_ms[4] = whole iteration (first event to last, launch gaps included).
 // Single-GPU, P = NULL path only (the configuration the roofline is quoted on).
 extern "C" int b200_cg_time_kernels(B200Cg *cg, double *d_x, int reps, double *out_ms) {
@@ -922,8 +929,8 @@ extern "C" int b200_cg_time_kernels(B200Cg *cg, double *d_x, int reps, double *o
       memset(&a, 0, sizeof(a));
       cudaEventRecord(ev[(size_t)r * 5 + 0], st);
       const bool re = cg->A_cg != nullptr && cg->At_cg != nullptr && cg->d_ry_cg != nullptr;
-      a.d_x = cg->d_p; a.d_y = cg->d_tmp; a.init_sign = 1.0; a.post = B200_POST_DIV;
-      a.d_d = re ? cg->d_ry_cg : cg->d_ry;
+      a.d_x = cg->d_p; a.d_y = cg->d_tmp; a.init_sign = 1.0; a.post = B200_POST_MUL;
+      a.d_d = re ? cg->d_ry_cg : cg->d_ry_inv;
       a.d_skip = d_skip;
       if (b200_spmv(re ? cg->A_cg : cg->A, &a) != 0) ok = false;
       cudaEventRecord(ev[(size_t)r * 5 + 1], st);

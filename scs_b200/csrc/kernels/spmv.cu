@@ -83,6 +83,8 @@ __device__ __forceinline__ void spmv_epilogue_pre(double s, int row, double *__r
   double out = s;
   if (POST == B200_POST_DIV) {
     out = s / dv;
+  } else if (POST == B200_POST_MUL) {
+    out = s * dv;
   } else if (POST == B200_POST_FMA_DOT) {
     out = fma(dv, vv, s);
     dot_acc = fma(vv, out, dot_acc);
@@ -99,6 +101,8 @@ __device__ __forceinline__ double spmv_epilogue(double s, int row, double *__res
   double out = s;
   if (POST == B200_POST_DIV) {
     out = s / d[row];
+  } else if (POST == B200_POST_MUL) {
+    out = s * d[row];
   } else if (POST == B200_POST_FMA_DOT) {
     const double vr = v[row];
     out = fma(d[row], vr, s);
@@ -952,6 +956,7 @@ static void spmv_set_attrs() {
   do {                                                                                           \
     cudaFuncSetAttribute(K<B200_POST_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES));    \
     cudaFuncSetAttribute(K<B200_POST_DIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES));     \
+    cudaFuncSetAttribute(K<B200_POST_MUL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES));     \
     cudaFuncSetAttribute(K<B200_POST_FMA_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES)); \
     cudaFuncSetAttribute(K<B200_POST_FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES));     \
   } while (0)
@@ -1489,6 +1494,7 @@ extern "C" int b200_spmv(const B200Spmv *M, const B200SpmvArgs *a) {
     switch (a->post) {
       case B200_POST_NONE: COMBINE(B200_POST_NONE); break;
       case B200_POST_DIV: COMBINE(B200_POST_DIV); break;
+      case B200_POST_MUL: COMBINE(B200_POST_MUL); break;
       case B200_POST_FMA_DOT: COMBINE(B200_POST_FMA_DOT); break;
       case B200_POST_FMA: COMBINE(B200_POST_FMA); break;
       default: return -1;
@@ -1501,6 +1507,7 @@ extern "C" int b200_spmv(const B200Spmv *M, const B200SpmvArgs *a) {
   switch (a->post) {
     case B200_POST_NONE: LAUNCH(B200_POST_NONE); break;
     case B200_POST_DIV: LAUNCH(B200_POST_DIV); break;
+    case B200_POST_MUL: LAUNCH(B200_POST_MUL); break;
     case B200_POST_FMA_DOT: LAUNCH(B200_POST_FMA_DOT); break;
     case B200_POST_FMA: LAUNCH(B200_POST_FMA); break;
     default: return -1;

@@ -23,6 +23,12 @@
  * All compute happens in hand-written sm_100a CUDA kernels; there is no CPU
  * fallback: every entry point fails (NULL / nonzero / SCS_FAILED) when no CUDA
  * device is usable.
+ *
+ * Threading: one process drives ONE GPU (SCS_B200_DEVICE / LOCAL_RANK) through ONE stream.  Entry points may be
+ * called from any host thread (each binds the calling thread to the library's device; the pinned staging buffer of
+ * pageable copies is mutex-protected), but work of different workspaces is ordered by that single stream and the
+ * kernel-launch sequence of a solve is not re-entrant: run one scs_solve / scs_solve_lin_sys at a time per
+ * process (the reference is re-entrant per ScsWork; this library is re-entrant per process).
  */
 #ifndef SCS_B200_H
 #define SCS_B200_H

@@ -577,7 +577,7 @@ scs_int scs_b200_time_cg_kernels(ScsLinSysWork *w, const scs_float *b, scs_int r
   const size_t nm = (size_t)w->n + w->m;
   const double nnz = (double)b200_spmv_nnz(w->A), n = (double)w->n, m = (double)w->m;
   int k;
-  if (w->nranks > 1 || w->P) return -1;
+  if (w->P) return -1;
   if (b200_h2d(w->d_b, b, nm * 8) != 0) return -1;
   if (b200_cg_solve(&w->cg, w->d_b, NULL, 0.0, 1, 0, NULL) < 0) return -1; /* genuine start: p, r, z, ctl */
   w->cg.h_ctl->done = 0;

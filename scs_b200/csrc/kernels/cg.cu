@@ -520,7 +520,7 @@ __device__ __forceinline__ void px_wait(volatile unsigned long long *line, int f
       if (clock64() - t0 > 3000000000LL) { ctl->pad[0] = 1; return; }
     }
   }
-  __threadfence_system();
+  asm volatile("fence.acq_rel.sys;" ::: "memory");  // acquire side: the peer's data stores precede its flag store
 }
 
 __global__ void __launch_bounds__(VEC_THREADS)
@@ -528,8 +528,10 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int y_has_px,
                 const double *__restrict__ rx, const double *__restrict__ M, double *p,
                 double *__restrict__ Gp, double *__restrict__ x, double *__restrict__ r,
                 double *__restrict__ z, B200CgCtl *ctl, double *partials, unsigned int *counters) {
+  pdl_launch_dependents();  // the next K1 may start its prologue; it waits for this grid before it gathers from p
+  pdl_wait();               // K2 (this rank's pushes and its "partial ready" signal) complete
   if (ctl->done || ctl->pad[0]) return;
-  __shared__ double s_red[128];
+  __shared__ double s_red[192];
   __shared__ double s_bc[4];
   const int G = pv.nranks, me = pv.rank;
   const int parity = (int)(seq & 1ull);
@@ -555,20 +557,17 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int y_has_px,
     acc = fma(pi, out, acc);
   }
   {
+    // slice total by the deterministic parallel last-block reduction (common.cuh grid_finish: fixed slots, fixed tree)
     double a[1] = {acc};
     block_sum<1>(a, s_red);
-    if (threadIdx.x == 0) {
-      partials[blockIdx.x] = a[0];
-      __threadfence();
-      if (atomicAdd(&counters[4], 1u) == gridDim.x - 1) {
-        counters[4] = 0u;
-        __threadfence();
-        double tot = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) tot += __ldcg(&partials[b]);  // block order
-        for (int q = 0; q < G; ++q) px_scal(pv, q, 0, parity, me)[0] = tot;
+    if (grid_finish<1>(a, partials, &counters[4], 0u, s_red)) {
+      if (threadIdx.x == 0) {
+        for (int q = 0; q < G; ++q) px_scal(pv, q, 0, parity, me)[0] = a[0];
         __threadfence_system();
         for (int q = 0; q < G; ++q) *((volatile unsigned long long *)(pv.flags[q] + 16 + me)) = seq;
       }
+    }
+    if (threadIdx.x == 0) {
       // ---- 2: all partial scalars -> alpha
       px_wait(myflags, 16, G, -1, seq, ctl);
       double pGp = 0.0;
@@ -597,26 +596,19 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int y_has_px,
     double sm[1] = {acc0}, mx[1] = {acc1};
     block_sum<1>(sm, s_red);
     block_max<1>(mx, s_red + 64);
-    if (threadIdx.x == 0) {
-      partials[2048 + blockIdx.x] = sm[0];
-      partials[4096 + blockIdx.x] = mx[0];
-      __threadfence();
-      if (atomicAdd(&counters[5], 1u) == gridDim.x - 1) {
-        counters[5] = 0u;
-        __threadfence();
-        double t0 = 0.0, t1 = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) {
-          t0 += __ldcg(&partials[2048 + b]);
-          t1 = fmax(t1, __ldcg(&partials[4096 + b]));
-        }
+    double both[2] = {sm[0], mx[0]};
+    if (grid_finish<2>(both, partials + 2048, &counters[5], 2u, s_red)) {
+      if (threadIdx.x == 0) {
         for (int q = 0; q < G; ++q) {
           double *sl = px_scal(pv, q, 1, parity, me);
-          sl[0] = t0;
-          sl[1] = t1;
+          sl[0] = both[0];
+          sl[1] = both[1];
         }
         __threadfence_system();
         for (int q = 0; q < G; ++q) *((volatile unsigned long long *)(pv.flags[q] + 24 + me)) = seq;
       }
+    }
+    if (threadIdx.x == 0) {
       // ---- 4: z'r, ||r||_inf, stop decision, beta (same arithmetic as k_cg_update's last block)
       px_wait(myflags, 24, G, -1, seq, ctl);
       double ztr = 0.0, rn = 0.0;
@@ -844,15 +836,18 @@ static int shard_x_active(const B200Cg *cg) {
   return g_shard_x == 1 && cg->nranks > 1 && cg->use_p2p && cg->d_p2p_route != nullptr;
 }
 
-static int cg_iteration_shard_x(B200Cg *cg, double *d_x) {
+static int cg_iteration_shard_x(B200Cg *cg, double *d_x, cudaEvent_t *ev = nullptr) {
   cudaStream_t st = (cudaStream_t)b200_stream();
   const int *d_skip = &cg->d_ctl->done;
+  if (ev) cudaEventRecord(ev[0], st);
   B200SpmvArgs a;
   memset(&a, 0, sizeof(a));
   // K1 (local rows): tmp_g = (A_g p) ./ R_g
+  a.pdl = cg_pdl_enabled() ? 1 : 0;
   a.d_x = cg->d_p; a.d_y = cg->d_tmp + cg->row0; a.init_sign = 1.0; a.post = B200_POST_MUL;
   a.d_d = cg->d_ry_inv + cg->row0; a.d_skip = d_skip;
   if (b200_spmv(cg->A, &a) != 0) return -1;
+  if (ev) cudaEventRecord(ev[1], st);
   // K2: partial A_g' tmp_g, every row pushed to its owner's inbox; the last block signals "partial ready"
   const unsigned long long seq = b200_p2p_next_seq();
   a.d_x = cg->d_tmp + cg->row0;
@@ -865,6 +860,7 @@ static int cg_iteration_shard_x(B200Cg *cg, double *d_x) {
     a.d_x = cg->d_p; a.d_y = cg->d_Gp; a.init_sign = 1.0; a.post = B200_POST_NONE; a.d_skip = d_skip;
     if (b200_spmv(cg->P, &a) != 0) return -1;
   }
+  if (ev) cudaEventRecord(ev[2], st);
   const int G = cg->nranks, me = b200_comm_rank();
   P2pViewX pv;
   pv.nranks = G; pv.rank = me; pv.S = (cg->n + G - 1) / G;
@@ -877,9 +873,10 @@ static int cg_iteration_shard_x(B200Cg *cg, double *d_x) {
   const long long slice = ((long long)cg->n + G - 1) / G;
   const long long want = (slice + VEC_THREADS - 1) / VEC_THREADS;
   if (want < g) g = (int)(want < 1 ? 1 : want);
-  k_cgx_iteration<<<g, VEC_THREADS, 0, st>>>(cg->n, pv, seq, cg->P != nullptr, cg->d_rx, cg->d_M, cg->d_p,
-                                             cg->d_Gp, d_x, cg->d_r, cg->d_z, cg->d_ctl, cg->d_partials,
-                                             cg->d_counter);
+  CUDA_OK(b200_launch(k_cgx_iteration, dim3(g), dim3(VEC_THREADS), 0, st, cg_pdl_enabled(), cg->n, pv, seq,
+                      (int)(cg->P != nullptr), (const double *)cg->d_rx, (const double *)cg->d_M, cg->d_p, cg->d_Gp,
+                      d_x, cg->d_r, cg->d_z, cg->d_ctl, cg->d_partials, cg->d_counter));
+  if (ev) cudaEventRecord(ev[3], st);
   b200_count_launch(1);
   return 0;
 }
@@ -910,6 +907,31 @@ extern "C" int b200_cg_one_iteration(B200Cg *cg, double *d_x) { return cg_iterat
 // K3 (k_cg_update), K4 (k_cg_pupdate); out_ms[4] = whole iteration (first event to last, launch gaps included).
 // Single-GPU, P = NULL path only (the configuration the roofline is quoted on).
 extern "C" int b200_cg_time_kernels(B200Cg *cg, double *d_x, int reps, double *out_ms) {
+  if (cg->nranks > 1 && shard_x_active(cg) && !cg->P && reps > 0) {
+    // sharded-x push mode: K1 (local rows), K2 (local partial + pushes + signal), K34 (the slice kernel incl. all waits
+    // on the peers); out_ms[3] = 0. Every rank runs this together (the kernels synchronise through the peer flags).
+    cudaStream_t st = (cudaStream_t)b200_stream();
+    std::vector<cudaEvent_t> ev((size_t)reps * 4);
+    for (auto &e : ev) cudaEventCreate(&e);
+    int rc = 0;
+    for (int r = 0; r < reps && rc == 0; ++r) rc = cg_iteration_shard_x(cg, d_x, &ev[(size_t)r * 4]);
+    if (cudaStreamSynchronize(st) != cudaSuccess) rc = -1;
+    if (rc == 0) {
+      for (int k = 0; k < 5; ++k) out_ms[k] = 0.0;
+      for (int r = 0; r < reps; ++r) {
+        float ms;
+        for (int k = 0; k < 3; ++k) {
+          cudaEventElapsedTime(&ms, ev[(size_t)r * 4 + k], ev[(size_t)r * 4 + k + 1]);
+          out_ms[k] += ms;
+        }
+        cudaEventElapsedTime(&ms, ev[(size_t)r * 4], ev[(size_t)r * 4 + 3]);
+        out_ms[4] += ms;
+      }
+      for (int k = 0; k < 5; ++k) out_ms[k] /= reps;
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
+  }
   if (cg->nranks > 1 || cg->P || reps <= 0) return -1;
   cudaStream_t st = (cudaStream_t)b200_stream();
   const int n = cg->n;

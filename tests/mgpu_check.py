@@ -85,14 +85,26 @@ if os.environ.get("MGPU_TIME", "1") != "0":
             print(f"[C2 sharded over {world} GPUs] CG iteration, {label}: {float(t[0])*1e3:.1f} us", flush=True)
     lib.scs_b200_set_p2p_mode(0)
     if os.environ.get("MGPU_SHARD_X"):
-        # STAGED mode (kernels/cg.cu k_cgx_iteration, not yet run on hardware): time it, then check a solve
+        # push-based sharded-x mode (kernels/cg.cu k_cgx_iteration): time it, then check a solve
         lib.scs_b200_set_shard_x.argtypes = [C.c_int]
         lib.scs_b200_set_shard_x(1)
         ms = lib.scs_b200_time_cg_iter(w, 30, C.byref(ab))
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if rank == 0:
-            print(f"[C2 sharded over {world} GPUs] CG iteration, sharded-x (staged): {float(t[0])*1e3:.1f} us", flush=True)
+            print(f"[C2 sharded over {world} GPUs] CG iteration, sharded-x push mode: {float(t[0])*1e3:.1f} us", flush=True)
+        # per-phase timeline (events between the kernels; the slice kernel's time includes every wait on the peers)
+        rhs_t = np.random.default_rng(5).standard_normal(n + m)
+        msv = (C.c_double * 5)()
+        byv = (C.c_double * 5)()
+        rc = lib.scs_b200_time_cg_kernels(w, capi.dptr(rhs_t), 30, msv, byv)
+        tt = torch.tensor([msv[0], msv[1], msv[2], msv[4]], device="cuda", dtype=torch.float64)
+        tmx = tt.clone()
+        dist.all_reduce(tmx, op=dist.ReduceOp.MAX)
+        if rank == 0 and rc == 0:
+            print(f"[C2 sharded over {world} GPUs] sharded-x phases (max over ranks, us): K1 local rows {float(tmx[0])*1e3:.1f} | "
+                  f"K2 local partial + push + signal {float(tmx[1])*1e3:.1f} | slice kernel (reduce, 2 scalar exchanges, K3/K4, "
+                  f"p push, waits) {float(tmx[2])*1e3:.1f} | iteration with events {float(tmx[3])*1e3:.1f}", flush=True)
         rng2 = np.random.default_rng(99)
         rhs = rng2.standard_normal(n + m)
         mine = rhs.copy()

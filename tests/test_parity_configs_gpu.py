@@ -31,9 +31,12 @@ pytestmark = pytest.mark.gpu
 # (config, scale): n, m, nnz at these scales: C2 1e4/3e4/1e5, C3 2.5e3/2.5e3/2.5e4 (box + LP), C4 5e3/5.55e4/1e6 with
 # 10 PSD blocks of order 100, C5 1e4/3e4/1.5e5 (50 SOCs + PSD blocks of order 10)
 CASES = [("C2", 0.01), ("C3", 0.002), ("C4", 0.05), ("C5", 0.005)]
-# C3 (LP with a box cone) needs 2850 ADMM iterations = minutes of CPU time at ANY scale the reference can run
-# (65 000 at n=2500): its converged comparison is replaced by a fixed-window trajectory comparison below
-CONVERGED = [c for c in CASES if c[0] != "C3"]
+# Converged comparisons are sized by the CPU reference on the GPU box's host (one C2 x0.01 solve takes it 70 s): C2 at
+# x0.004 with and without Anderson acceleration; C4 and C5 with the default settings only. C3 (LP with a box cone) needs
+# 2850 ADMM iterations = minutes of CPU time at ANY scale the reference can run (65 000 at n=2500): its converged
+# comparison is replaced by a fixed-window trajectory comparison below. The round-2 run at the larger scales (C2 x0.01,
+# C4 x0.05, C5 x0.005, both AA settings) is kept in profiles/r02c_device_setup_reorder_parity.log.
+CONVERGED = [("C2", 0.004, 0), ("C2", 0.004, 10), ("C4", 0.05, 10), ("C5", 0.003, 10)]
 
 
 def solve(lib, prob, **over):
@@ -90,8 +93,7 @@ def test_config_one_iteration_1e10(lib, reflib, cfg, scale):
         assert v <= gate, (cfg, k, v, gate)
 
 
-@pytest.mark.parametrize("cfg,scale", CONVERGED)
-@pytest.mark.parametrize("aa", [0, 10])
+@pytest.mark.parametrize("cfg,scale,aa", CONVERGED)
 def test_config_default_solve_matches_reference(lib, reflib, cfg, scale, aa):
     prob = problems.config(cfg, scale=scale)
     over = dict(acceleration_lookback=aa)
@@ -155,9 +157,14 @@ def test_c3_fixed_window_trajectory_matches_reference(lib, reflib):
         assert v <= gate, (k, v, gate)
 
 
-def test_full_size_c2_kkt_solve_vs_reference(lib):
-    """scs_solve_lin_sys at tol 1e-12 on the FULL C2 operator (n=1e6, m=3e6, nnz=1e7) against the reference's
-    CPU-indirect backend (OpenMP build for the SpMV, ~1 min of host time): <= 1e-10 relative."""
+@pytest.mark.parametrize("full", [pytest.param(False, id="C2x0.1"), pytest.param(True, id="C2full")])
+def test_c2_kkt_solve_vs_reference(lib, full):
+    """scs_solve_lin_sys at tol 1e-12 on the C2 operator against the reference's CPU-indirect backend (OpenMP build for
+    the SpMV): <= 1e-10 relative. The FULL size (n=1e6, m=3e6, nnz=1e7) costs the reference ~5 min of host time on the
+    GPU box: it runs only with SCS_B200_SLOW_TESTS=1 (round-2 result: 2004 CG iterations, x 4.4e-14, y 5.2e-14,
+    profiles/r02c_device_setup_reorder_parity.log); the default run does the same test at a tenth of the size."""
+    if full and not os.environ.get("SCS_B200_SLOW_TESTS"):
+        pytest.skip("full-size C2 reference solve takes minutes of host time: set SCS_B200_SLOW_TESTS=1")
     omp = os.path.join(REF_DIR, "libscsindir_ref_omp.so")
     plain = os.path.join(REF_DIR, "libscsindir_ref.so")
     path = omp if os.path.exists(omp) else plain
@@ -166,10 +173,11 @@ def test_full_size_c2_kkt_solve_vs_reference(lib):
     os.environ.setdefault("OMP_NUM_THREADS", str(min(32, os.cpu_count() or 1)))
     ref = capi.load_reference(path)
     rng = np.random.default_rng(1234)
-    n, m = 1_000_000, 3_000_000
+    n = 1_000_000 if full else 100_000
+    m = 3 * n
     A = problems.random_sparse_csc(m, n, 10, rng)
     hp = capi.HostProblem(A, np.zeros(m), np.zeros(n), {"l": m})
-    z = 300_000
+    z = m // 10
     dr = np.empty(n + m + 1)
     dr[:n], dr[n:n + z], dr[n + z:] = 1e-6, 1.0 / 100.0, 10.0
     rhs = rng.standard_normal(n + m)
@@ -194,7 +202,7 @@ def test_full_size_c2_kkt_solve_vs_reference(lib):
     lhs = dr[:n] * xs + problems.csc_rmatvec(A, t)
     rr = rhs[:n] + problems.csc_rmatvec(A, rhs[n:] / dr[n:n + m])
     res = float(np.abs(lhs - rr).max())
-    print(f"\n[C2 full KKT solve tol 1e-12] ours {its} CG iterations {t_m:.2f}s (incl. H2D/D2H) | reference {t_r:.1f}s | "
+    print(f"\n[C2 {'full' if full else 'x0.1'} KKT solve tol 1e-12] ours {its} CG iterations {t_m:.2f}s (incl. H2D/D2H) | reference {t_r:.1f}s | "
           f"rel err x {ex:.2e} y {ey:.2e} | reduced residual (host fp64) {res:.2e}")
     assert ex <= 1e-10 and ey <= 1e-10
     assert res <= 1e-10

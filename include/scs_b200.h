@@ -188,7 +188,9 @@ double scs_b200_time_cg_iter(ScsLinSysWork *w, scs_int reps, double *alg_bytes);
  * on the host right-hand side b, length n+m), each bracketed by CUDA events on the library stream:
  * out_ms[0..4] = ms per launch of K1 (tmp = R_y^-1 A p), K2 (Gp = R_x p + A' tmp, p'Gp, alpha), K3 (x, r, z update
  * + reductions), K4 (p update) and of the whole iteration; out_bytes[0..4] = algorithmic bytes of each
- * (reference path: linsys/cpu/indirect/private.c:106-119,174-214). Single GPU, P = NULL. 0 on success. */
+ * (reference path: linsys/cpu/indirect/private.c:106-119,174-214). P = NULL. 0 on success. out_ms must hold 12
+ * doubles: on several GPUs (sharded-x push mode, all ranks call together) out_ms[0..2] = K1, K2 (with its NVLink
+ * pushes), the slice kernel; [3] = 0; [4] = iteration; [5..11] = the phases inside the slice kernel (rank-local). */
 scs_int scs_b200_time_cg_kernels(ScsLinSysWork *w, const scs_float *b, scs_int reps, double *out_ms,
                                  double *out_bytes);
 

@@ -205,6 +205,25 @@ static inline cudaError_t b200_launch(void (*kernel)(KArgs...), dim3 grid, dim3 
 }
 #endif
 
+// ---------------------------------------------------------------- self-validating 16-byte messages (multi-GPU)
+// A double travels as two 8-byte words, each carrying the 32-bit sequence number of the exchange in its upper half
+// (NCCL's "LL" scheme): an 8-byte store is atomic, so a reader that sees the expected sequence number in BOTH words has
+// the whole value -- no fence and no separate flag on either side.
+__device__ __forceinline__ void ll_store(unsigned long long *dst2, double v, unsigned seq32) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long w0 = (b & 0xffffffffull) | ((unsigned long long)seq32 << 32);
+  const unsigned long long w1 = (b >> 32) | ((unsigned long long)seq32 << 32);
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst2), "l"(w0), "l"(w1) : "memory");
+}
+// returns true and the value once both halves carry seq32
+__device__ __forceinline__ bool ll_try_load(const unsigned long long *src2, unsigned seq32, double &v) {
+  unsigned long long w0, w1;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src2) : "memory");
+  if ((unsigned)(w0 >> 32) != seq32 || (unsigned)(w1 >> 32) != seq32) return false;
+  v = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+  return true;
+}
+
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

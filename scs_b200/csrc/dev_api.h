@@ -75,14 +75,16 @@ typedef struct {
 } B200P2pSignal;
 
 /* B200_HOOK_P2P_ROUTE (POST_NONE only, flagged-stream kernel): output row j is not stored to d_y but PUSHED over
- * NVLink into the inbox of the rank that owns slice [lo[o], lo[o+1]) of the output space: dst[o][j - lo[o]]
- * (dst[o] = this rank's lane of rank o's inbox as mapped in this process; lo[nranks] = nrows). When the last
- * block has stored its rows it publishes hook_val into slot `rank` of every peer's flag line, like
- * B200_HOOK_P2P_SIGNAL. The SpMV thereby IS the reduce-scatter send of the sharded-x CG (kernels/cg.cu). */
+ * NVLink into the inbox of the rank that owns slice [lo[o], lo[o+1]) of the output space, as a 16-byte SELF-VALIDATING
+ * element: {low 32 bits of the double | seq << 32, high 32 bits | seq << 32} with seq = the low 32 bits of hook_val
+ * (the scheme of NCCL's LL protocol: every 8-byte half carries its own flag, so the receiver needs no fence, no
+ * separate "ready" flag and can start summing while rows are still arriving). dst[o] = this rank's lane of rank o's
+ * inbox as mapped in this process (element j - lo[o]); lo[nranks] = nrows. The SpMV thereby IS the reduce-scatter
+ * send of the sharded-x CG (kernels/cg.cu). */
 typedef struct {
   int nranks, rank;
   int lo[9];
-  double *dst[8];
+  unsigned long long *dst[8];
   unsigned long long *flags[8];
 } B200P2pRoute;
 
@@ -181,7 +183,7 @@ int b200_p2p_stride(void);
 double *b200_p2p_base(int r);
 unsigned long long *b200_p2p_flags(int r);
 double *b200_p2p_pvec(int r);   /* rank r's p vector inside its exchange allocation (sharded-x mode) */
-double *b200_p2p_inbox(int r);  /* rank r's inbox [G][ceil(n/G)] */
+double *b200_p2p_inbox(int r);  /* rank r's inbox [G][ceil(n/G)] of 16-byte elements (2 doubles of storage each) */
 int b200_p2p_claim_pvec(void);  /* the exchange p vector serves one workspace at a time; 0 = claimed */
 void b200_p2p_release_pvec(void);
 unsigned long long b200_p2p_next_seq(void);

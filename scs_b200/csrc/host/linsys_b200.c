@@ -402,7 +402,7 @@ ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
       rt.nranks = G; rt.rank = w->rank;
       for (r = 0; r <= G; ++r) rt.lo[r] = (int)(((long long)n * r) / G);
       for (r = 0; r < G; ++r) {
-        rt.dst[r] = b200_p2p_inbox(r) + (size_t)w->rank * S; /* my lane of rank r's inbox */
+        rt.dst[r] = (unsigned long long *)b200_p2p_inbox(r) + 2 * (size_t)w->rank * S; /* my lane of rank r's inbox */
         rt.flags[r] = b200_p2p_flags(r);
       }
       w->p_in_exchange = 1;

@@ -481,11 +481,13 @@ k_cg_finish_p2p2(int n, double *__restrict__ y, P2pView pv, unsigned long long s
 // pipeline; remote loads pay the full round trip), synchronisation is by sequence-numbered flags:
 //   K1  tmp_g = R_g^-1 A_g p                                   local SpMV
 //   K2  partial_g = A_g' tmp_g, every output row pushed into the inbox of the rank that owns it by the SpMV
-//       epilogue itself (B200_HOOK_P2P_ROUTE = the reduce-scatter send); its last block publishes "partial ready"
+//       epilogue itself (B200_HOOK_P2P_ROUTE = the reduce-scatter send) as a SELF-VALIDATING 16-byte element (value
+//       halves + sequence number, common.cuh ll_store): no fence, no "ready" flag, no end-of-kernel signal
 //   K34 ONE kernel per rank (this one):
-//       1  wait for the G-1 peer partials; sum MY slice from the LOCAL inbox in rank order, Gp = R_x p (+ P p) + sum,
-//          block-reduce p'Gp over the slice; the last block pushes the slice's p'Gp to every rank;
-//       2  wait for the G partial scalars, add them in rank order => p'Gp and alpha, identical bits everywhere;
+//       1  sum MY slice from the LOCAL inbox in rank order, waiting per element for rows still in flight,
+//          Gp = R_x p (+ P p) + sum, block-reduce p'Gp over the slice; the last block sends the slice's p'Gp to every
+//          rank as a self-validating scalar message;
+//       2  collect the G partial scalars, add them in rank order => p'Gp and alpha, identical bits everywhere;
 //       3  K3 on the slice (x, r, z; z'r and ||r||_inf partials), pushed the same way;
 //       4  wait, combine => z'r, ||r||_inf, the stop decision and beta, identical everywhere;
 //       5  K4 on the slice: p = z + beta p, stored into EVERY rank's p (the all-gather is G-1 remote stores per
@@ -496,17 +498,38 @@ k_cg_finish_p2p2(int n, double *__restrict__ y, P2pView pv, unsigned long long s
 // (tests/test_shardx_protocol_cpu.py emulates the protocol with threads and random delays).
 // Remote volume per rank and iteration: 2 (G-1)/G n doubles OUT; K3 / K4 shrink by G. All blocks spin on flags, so
 // the grid must be co-resident (<= #SMs blocks).
-// Exchange allocation (comm.cu): [0, 4n) buffers of the replicated modes, [4n, 5n) p, [5n, 6n+16) inbox
-// [G][S] with S = ceil(n / G), then the flag line (slots 0..7 "partial", 16..23 / 24..31 "scalars of round 1 / 2",
-// 32..39 "p slice") and 64 doubles of scalar slots [round][parity][rank][2].
+// Exchange allocation (comm.cu): [0, 4n) buffers of the replicated modes, [4n, 5n) p, [5n, 7n+32) inbox
+// [G][S][2 words] with S = ceil(n / G), then the flag line (slots 32..39 "p slice") and 64 words of scalar messages
+// [round][from rank][4].
 struct P2pViewX {
   int nranks, rank, S;
-  const double *inbox;          // local: inbox[q * S + (i - lo)] = rank q's partial for my element i
-  double *peer_p[8];            // peer_p[q]: rank q's p vector as mapped here (peer_p[rank] == local p)
+  const unsigned long long *inbox;  // local: element (q * S + i - lo) = rank q's partial for my element i (16 bytes)
+  double *peer_p[8];                // peer_p[q]: rank q's p vector as mapped here (peer_p[rank] == local p)
   unsigned long long *flags[8];
+  unsigned long long *dbg;          // optional: 8 globaltimer stamps (ns) of block 0 at the phase boundaries, or NULL
 };
-__device__ __forceinline__ double *px_scal(const P2pViewX &pv, int r, int round, int parity, int from) {
-  return reinterpret_cast<double *>(pv.flags[r] + 64) + (((round * 2 + parity) * 8 + from) * 2);
+__device__ __forceinline__ void px_stamp(const P2pViewX &pv, int k) {
+  if (pv.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    pv.dbg[k] = t;
+  }
+}
+// scalar messages: after the 64 flags of every rank's line, 64 words = [round 0..1][from rank 0..7][4 words]
+// (a double = 2 self-validating words; round 0 carries 1 double, round 1 carries 2)
+__device__ __forceinline__ unsigned long long *px_msg(const P2pViewX &pv, int r, int round, int from) {
+  return pv.flags[r] + 64 + (round * 8 + from) * 4;
+}
+// spin until the self-validating element carries seq32; gives up after ~1.5 s and raises the sticky error flag
+__device__ __forceinline__ double ll_wait(const unsigned long long *src2, unsigned seq32, B200CgCtl *ctl) {
+  double v = 0.0;
+  if (ll_try_load(src2, seq32, v)) return v;
+  const long long t0 = clock64();
+  while (!ll_try_load(src2, seq32, v)) {
+    if (*((volatile int *)&ctl->pad[0])) return 0.0;
+    if (clock64() - t0 > 3000000000LL) { ctl->pad[0] = 1; return 0.0; }
+  }
+  return v;
 }
 __device__ __forceinline__ void px_wait(volatile unsigned long long *line, int first, int G, int skip_rank,
                                         unsigned long long seq, B200CgCtl *ctl) {
@@ -529,12 +552,12 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int y_has_px,
                 double *__restrict__ Gp, double *__restrict__ x, double *__restrict__ r,
                 double *__restrict__ z, B200CgCtl *ctl, double *partials, unsigned int *counters) {
   pdl_launch_dependents();  // the next K1 may start its prologue; it waits for this grid before it gathers from p
-  pdl_wait();               // K2 (this rank's pushes and its "partial ready" signal) complete
+  pdl_wait();               // K2 (this rank's pushes) complete
   if (ctl->done || ctl->pad[0]) return;
   __shared__ double s_red[192];
   __shared__ double s_bc[4];
   const int G = pv.nranks, me = pv.rank;
-  const int parity = (int)(seq & 1ull);
+  const unsigned seq32 = (unsigned)seq;
   const long long lo = (long long)n * me / G, hi = (long long)n * (me + 1) / G;
   const long long gstride = (long long)gridDim.x * blockDim.x;
   const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -543,40 +566,39 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int y_has_px,
   const double ztr_old = ctl->ztr, tol = ctl->tol;
   const int iters_old = ctl->iters, max_its = ctl->max_its;
 
-  // ---- 1: peer partials have landed in my inbox -> my slice of G p, partial p'Gp
-  if (threadIdx.x == 0) px_wait(myflags, 0, G, me, seq, ctl);
-  __syncthreads();
+  px_stamp(pv, 0);
+  // ---- 1: my slice of G p from the self-validating rows in my inbox (rank order; a row that has not arrived yet is
+  // simply waited for -- the reduction overlaps the tail of the peers' K2), partial p'Gp
   double acc = 0.0;
   for (long long i = lo + gtid; i < hi; i += gstride) {
     double sum = 0.0;
-    for (int q = 0; q < G; ++q) sum += __ldcg(pv.inbox + (size_t)q * pv.S + (i - lo));  // rank order
+    for (int q = 0; q < G; ++q) sum += ll_wait(pv.inbox + 2 * ((size_t)q * pv.S + (size_t)(i - lo)), seq32, ctl);
     const double base = y_has_px ? Gp[i] + sum : sum;
     const double pi = p[i];
     const double out = fma(rx[i], pi, base);
     Gp[i] = out;
     acc = fma(pi, out, acc);
   }
+  px_stamp(pv, 1);
   {
-    // slice total by the deterministic parallel last-block reduction (common.cuh grid_finish: fixed slots, fixed tree)
+    // slice total by the deterministic parallel last-block reduction (common.cuh grid_finish: fixed slots, fixed tree),
+    // then one self-validating message to every rank (no fence, no flag)
     double a[1] = {acc};
     block_sum<1>(a, s_red);
     if (grid_finish<1>(a, partials, &counters[4], 0u, s_red)) {
-      if (threadIdx.x == 0) {
-        for (int q = 0; q < G; ++q) px_scal(pv, q, 0, parity, me)[0] = a[0];
-        __threadfence_system();
-        for (int q = 0; q < G; ++q) *((volatile unsigned long long *)(pv.flags[q] + 16 + me)) = seq;
-      }
+      if (threadIdx.x == 0)
+        for (int q = 0; q < G; ++q) ll_store(px_msg(pv, q, 0, me), a[0], seq32);
     }
     if (threadIdx.x == 0) {
-      // ---- 2: all partial scalars -> alpha
-      px_wait(myflags, 16, G, -1, seq, ctl);
+      // ---- 2: all partial scalars -> alpha (rank order: identical bits on every rank)
       double pGp = 0.0;
-      for (int q = 0; q < G; ++q) pGp += *((volatile double *)px_scal(pv, me, 0, parity, q));
+      for (int q = 0; q < G; ++q) pGp += ll_wait(px_msg(pv, me, 0, q), seq32, ctl);
       s_bc[0] = pGp;
       s_bc[1] = ztr_old / pGp;
     }
   }
   __syncthreads();
+  px_stamp(pv, 2);
   const double pGp = s_bc[0], alpha = s_bc[1], nalpha = -alpha;
 
   // ---- 3: K3 on the slice
@@ -592,30 +614,25 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int y_has_px,
     acc0 = fma(zi, ri, acc0);
     acc1 = fmax(acc1, fabs(ri));
   }
+  px_stamp(pv, 3);
   {
     double sm[1] = {acc0}, mx[1] = {acc1};
     block_sum<1>(sm, s_red);
     block_max<1>(mx, s_red + 64);
     double both[2] = {sm[0], mx[0]};
     if (grid_finish<2>(both, partials + 2048, &counters[5], 2u, s_red)) {
-      if (threadIdx.x == 0) {
+      if (threadIdx.x == 0)
         for (int q = 0; q < G; ++q) {
-          double *sl = px_scal(pv, q, 1, parity, me);
-          sl[0] = both[0];
-          sl[1] = both[1];
+          ll_store(px_msg(pv, q, 1, me), both[0], seq32);
+          ll_store(px_msg(pv, q, 1, me) + 2, both[1], seq32);
         }
-        __threadfence_system();
-        for (int q = 0; q < G; ++q) *((volatile unsigned long long *)(pv.flags[q] + 24 + me)) = seq;
-      }
     }
     if (threadIdx.x == 0) {
       // ---- 4: z'r, ||r||_inf, stop decision, beta (same arithmetic as k_cg_update's last block)
-      px_wait(myflags, 24, G, -1, seq, ctl);
       double ztr = 0.0, rn = 0.0;
       for (int q = 0; q < G; ++q) {
-        volatile double *sl = px_scal(pv, me, 1, parity, q);
-        ztr += sl[0];
-        rn = fmax(rn, sl[1]);
+        ztr += ll_wait(px_msg(pv, me, 1, q), seq32, ctl);
+        rn = fmax(rn, ll_wait(px_msg(pv, me, 1, q) + 2, seq32, ctl));
       }
       int done = 0;
       double beta = 0.0;
@@ -632,6 +649,7 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int y_has_px,
     }
   }
   __syncthreads();
+  px_stamp(pv, 4);
   const double ztr_new = s_bc[0], rnorm = s_bc[1], beta = s_bc[2];
   const int done = s_bc[3] != 0.0;
 
@@ -643,8 +661,9 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int y_has_px,
     }
   }
   __syncthreads();
+  px_stamp(pv, 5);
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    asm volatile("fence.acq_rel.sys;" ::: "memory");  // release: this block's p stores before its ticket
     if (atomicAdd(&counters[6], 1u) == gridDim.x - 1) {
       counters[6] = 0u;
       ctl->ztr_prev = ztr_old;
@@ -655,11 +674,13 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int y_has_px,
       ctl->iters = iters_old + 1;
       if (!done) ctl->beta = beta;
       if (done) ctl->done = 1;
-      __threadfence_system();
+      asm volatile("fence.acq_rel.sys;" ::: "memory");
       for (int q = 0; q < G; ++q) *((volatile unsigned long long *)(pv.flags[q] + 32 + me)) = seq;
     }
+    px_stamp(pv, 6);
     // ---- 6: the peers' slices of the new p have landed in my p
     if (!done) px_wait(myflags, 32, G, me, seq, ctl);
+    px_stamp(pv, 7);
   }
   __syncthreads();
 }
@@ -864,11 +885,12 @@ static int cg_iteration_shard_x(B200Cg *cg, double *d_x, cudaEvent_t *ev = nullp
   const int G = cg->nranks, me = b200_comm_rank();
   P2pViewX pv;
   pv.nranks = G; pv.rank = me; pv.S = (cg->n + G - 1) / G;
-  pv.inbox = b200_p2p_inbox(me);
+  pv.inbox = (const unsigned long long *)b200_p2p_inbox(me);
   for (int r = 0; r < 8; ++r) {
     pv.peer_p[r] = r < G ? b200_p2p_pvec(r) : nullptr;
     pv.flags[r] = r < G ? b200_p2p_flags(r) : nullptr;
   }
+  pv.dbg = ev ? reinterpret_cast<unsigned long long *>(cg->d_partials + 3 * 2048) : nullptr;  // timing runs only
   int g = b200_num_sms();  // every block spins on flags: one block per SM, co-resident
   const long long slice = ((long long)cg->n + G - 1) / G;
   const long long want = (slice + VEC_THREADS - 1) / VEC_THREADS;
@@ -928,6 +950,10 @@ extern "C" int b200_cg_time_kernels(B200Cg *cg, double *d_x, int reps, double *o
         out_ms[4] += ms;
       }
       for (int k = 0; k < 5; ++k) out_ms[k] /= reps;
+      // phase boundaries inside the slice kernel of the LAST timed iteration (block 0, globaltimer ns)
+      unsigned long long h[8];
+      if (cudaMemcpy(h, cg->d_partials + 3 * 2048, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
+        for (int k = 0; k < 7; ++k) out_ms[5 + k] = (double)(long long)(h[k + 1] - h[k]) * 1e-6;
     }
     for (auto &e : ev) cudaEventDestroy(e);
     return rc;

@@ -422,7 +422,7 @@ spmv_flag_kernel(const int *__restrict__ colidx, const double *__restrict__ vals
   const int nt = cta_begin[blockIdx.x + 1] - g_begin;
   // multi-GPU push mode: the routing table (static device data, written once at setup)
   __shared__ int s_rt_lo[9];
-  __shared__ double *s_rt_dst[8];
+  __shared__ unsigned long long *s_rt_dst[8];
   const bool routed = (POST == B200_POST_NONE) && hook == B200_HOOK_P2P_ROUTE;
   if (routed && tid < 9) {
     const B200P2pRoute *rt = reinterpret_cast<const B200P2pRoute *>(hook_arg);
@@ -617,10 +617,10 @@ spmv_flag_kernel(const int *__restrict__ colidx, const double *__restrict__ vals
             iv0 = (init != nullptr) ? init[row] : 0.0;
           }
           if (init != nullptr) sres = __dadd_rn(sres, init_sign * iv0);
-          if (routed) {  // push the row to the rank that owns it (a warp-tile spans at most a few owners)
+          if (routed) {  // push the row to the rank that owns it, as a self-validating 16-byte element
             int o = 0;
             while (row >= s_rt_lo[o + 1]) ++o;
-            s_rt_dst[o][row - s_rt_lo[o]] = sres;
+            ll_store(s_rt_dst[o] + 2 * (size_t)(row - s_rt_lo[o]), sres, (unsigned)hook_val);
           } else {
             spmv_epilogue_pre<POST>(sres, row, y, dv, vv, dot_acc);
           }
@@ -631,25 +631,19 @@ spmv_flag_kernel(const int *__restrict__ colidx, const double *__restrict__ vals
   }
 
   if (skipped) return;  // uniform over the CTA: every thread read the same *skip after the predecessor completed
-  if (hook == B200_HOOK_P2P_SIGNAL || routed) {
-    // multi-GPU: tell every peer that this rank's partial product is complete (last block only). In push mode the
-    // rows were stored into PEER memory: every block orders its stores system-wide before it takes its ticket.
+  if (hook == B200_HOOK_P2P_SIGNAL) {
+    // multi-GPU (replicated modes): tell every peer that this rank's partial product is complete (last block only).
+    // The push mode (B200_HOOK_P2P_ROUTE) needs no signal: every pushed row validates itself.
     __syncthreads();
     if (threadIdx.x == 0) {
-      if (routed) __threadfence_system(); else __threadfence();
+      __threadfence();
       const unsigned tk = atomicAdd(counter, 1u);
       if (tk == gridDim.x - 1) {
         *counter = 0u;
         __threadfence_system();
-        if (routed) {
-          const B200P2pRoute *rt = reinterpret_cast<const B200P2pRoute *>(hook_arg);
-          for (int r = 0; r < rt->nranks; ++r)
-            if (r != rt->rank) *((volatile unsigned long long *)(rt->flags[r] + rt->rank)) = hook_val;
-        } else {
-          const B200P2pSignal *ps = reinterpret_cast<const B200P2pSignal *>(hook_arg);
-          for (int r = 0; r < ps->nranks; ++r)
-            if (r != ps->rank) *((volatile unsigned long long *)(ps->flags[r] + ps->rank)) = hook_val;
-        }
+        const B200P2pSignal *ps = reinterpret_cast<const B200P2pSignal *>(hook_arg);
+        for (int r = 0; r < ps->nranks; ++r)
+          if (r != ps->rank) *((volatile unsigned long long *)(ps->flags[r] + ps->rank)) = hook_val;
       }
     }
   }

@@ -95,7 +95,7 @@ if os.environ.get("MGPU_TIME", "1") != "0":
             print(f"[C2 sharded over {world} GPUs] CG iteration, sharded-x push mode: {float(t[0])*1e3:.1f} us", flush=True)
         # per-phase timeline (events between the kernels; the slice kernel's time includes every wait on the peers)
         rhs_t = np.random.default_rng(5).standard_normal(n + m)
-        msv = (C.c_double * 5)()
+        msv = (C.c_double * 12)()
         byv = (C.c_double * 5)()
         rc = lib.scs_b200_time_cg_kernels(w, capi.dptr(rhs_t), 30, msv, byv)
         tt = torch.tensor([msv[0], msv[1], msv[2], msv[4]], device="cuda", dtype=torch.float64)
@@ -105,6 +105,10 @@ if os.environ.get("MGPU_TIME", "1") != "0":
             print(f"[C2 sharded over {world} GPUs] sharded-x phases (max over ranks, us): K1 local rows {float(tmx[0])*1e3:.1f} | "
                   f"K2 local partial + push + signal {float(tmx[1])*1e3:.1f} | slice kernel (reduce, 2 scalar exchanges, K3/K4, "
                   f"p push, waits) {float(tmx[2])*1e3:.1f} | iteration with events {float(tmx[3])*1e3:.1f}", flush=True)
+            names = ("reduce slice (waits for rows in flight)", "slice dot: grid reduction + scalar exchange 1", "K3 on the slice",
+                     "grid reduction + scalar exchange 2", "K4 on the slice + p push", "release fence + ticket", "wait for the peers' p slices")
+            print(f"[C2 sharded over {world} GPUs] inside the slice kernel, rank 0 block 0, last iteration (us): " +
+                  " | ".join(f"{nm} {msv[5 + k]*1e3:.1f}" for k, nm in enumerate(names)), flush=True)
         rng2 = np.random.default_rng(99)
         rhs = rng2.standard_normal(n + m)
         mine = rhs.copy()

@@ -1,11 +1,12 @@
 """CPU emulation of the PUSH-based "sharded-x" multi-GPU CG iteration (scs_b200/csrc/kernels/cg.cu:
 k_cgx_iteration + cg_iteration_shard_x, scs_b200/csrc/kernels/spmv.cu B200_HOOK_P2P_ROUTE). Every rank is a Python
 thread; the exchange allocations (inbox [G][S], the p vector), flag lines and scalar slots are shared numpy arrays laid
-out like the device buffers (flag slots 0.. "partial", 16.. / 24.. "scalars of round 1 / 2", 32.. "p slice", scalar
-slots [round][parity][rank][2]). Data moves only by STORES into the peer's arrays, exactly as on the device: the K2
-SpMV pushes each output row into the owner's inbox, K4 stores the new p slice into every rank's p. The emulation
-follows the kernel phase by phase -- same slot arithmetic, same rank-order sums, same stop logic, NO double buffering
-of inbox / p -- and checks: no deadlock, no torn reads under random delays (ranks run up to an iteration apart), all
+out like the device buffers. Data moves only by STORES into the peer's arrays, exactly as on the device: the K2 SpMV
+pushes each output row into the owner's inbox as a SELF-VALIDATING element (value + the sequence number of the exchange,
+common.cuh ll_store: no "partial ready" flag exists, the reader waits per element), the partial scalars travel the same
+way, K4 stores the new p slice into every rank's p followed by the only flag of the protocol (slot 32 + rank). The
+emulation follows the kernel phase by phase -- same rank-order sums, same stop logic, NO double buffering of inbox,
+messages or p, writes of one push deliberately split in two halves with a delay between them -- and checks: no deadlock, no torn reads under random delays (ranks run up to an iteration apart), all
 ranks hold bit-identical p / alpha / beta / stop decisions, and the iterates agree with a plain single-process
 preconditioned CG on the same operator (reference linsys/cpu/indirect/private.c:133-217).
 It validates the PROTOCOL (what the blocks of one rank do together is one thread here); the CUDA-level parts
@@ -63,39 +64,37 @@ class Rank(threading.Thread):
         G, me, n, sh = self.G, self.me, self.n, self.sh
         if self.ctl["done"]:
             return
-        parity = seq & 1
         lo, hi = self.lo, self.hi
         S = (n + G - 1) // G
-        # K1 / K2: the rank's partial, every output row PUSHED into the inbox of its owner (lane `me`), then
-        # "partial ready" to the peers
+        # K1 / K2: the rank's partial, every output row PUSHED into the inbox of its owner (lane `me`) as (value, seq);
+        # no flag follows. The push is split in two halves with a pause in between: readers must cope with rows that
+        # have not arrived yet
         part = self.A.T @ (self.d * (self.A @ self.p))
-        for q in range(G):
-            qlo, qhi = n * q // G, n * (q + 1) // G
-            sh["inbox"][q][me * S:me * S + (qhi - qlo)] = part[qlo:qhi]
-        for q in range(G):
-            if q != me:
-                sh["flags"][q][me] = seq
+        for half in (0, 1):
+            for q in range(G):
+                qlo, qhi = n * q // G, n * (q + 1) // G
+                mid = (qhi - qlo) // 2
+                a, b = (0, mid) if half == 0 else (mid, qhi - qlo)
+                sh["inbox_val"][q][me * S + a:me * S + b] = part[qlo + a:qlo + b]
+                sh["inbox_seq"][q][me * S + a:me * S + b] = seq
+            self.pause()
         ztr_old, iters_old = self.ctl["ztr"], self.ctl["iters"]
-        self.pause()
-        # 1: wait for the peers' partials, reduce my slice from MY inbox in rank order
-        self.wait(0, me, seq)
+        # 1: reduce my slice from MY inbox in rank order, waiting per element for rows still in flight
         s = np.zeros(hi - lo)
         for q in range(G):
-            s = s + sh["inbox"][me][q * S:q * S + (hi - lo)]
+            self.wait_elems(sh["inbox_seq"][me], q * S, q * S + (hi - lo), seq)
+            s = s + sh["inbox_val"][me][q * S:q * S + (hi - lo)]
         self.Gp[lo:hi] = self.rx[lo:hi] * self.p[lo:hi] + s
         mine = float(self.p[lo:hi] @ self.Gp[lo:hi])
         for q in range(G):
-            arr, base = self.scal(q, 0, parity, me)
-            arr[base] = mine
-        for q in range(G):
-            sh["flags"][q][16 + me] = seq
+            sh["msg_val"][q][0 * 16 + me * 2] = mine
+            sh["msg_seq"][q][0 * 16 + me * 2] = seq
         self.pause()
         # 2: all partial scalars -> alpha
-        self.wait(16, -1, seq)
         pGp = 0.0
         for q in range(G):
-            arr, base = self.scal(me, 0, parity, q)
-            pGp += arr[base]
+            self.wait_elems(sh["msg_seq"][me], q * 2, q * 2 + 1, seq)
+            pGp += sh["msg_val"][me][q * 2]
         alpha = ztr_old / pGp
         self.pause()
         # 3: K3 on the slice
@@ -105,18 +104,17 @@ class Rank(threading.Thread):
         t0 = float(self.z[lo:hi] @ self.r[lo:hi])
         t1 = float(np.abs(self.r[lo:hi]).max()) if hi > lo else 0.0
         for q in range(G):
-            arr, base = self.scal(q, 1, parity, me)
-            arr[base], arr[base + 1] = t0, t1
-        for q in range(G):
-            sh["flags"][q][24 + me] = seq
+            base = 16 + me * 2
+            sh["msg_val"][q][base], sh["msg_val"][q][base + 1] = t0, t1
+            sh["msg_seq"][q][base], sh["msg_seq"][q][base + 1] = seq, seq
         self.pause()
         # 4: z'r, ||r||_inf, stop decision, beta
-        self.wait(24, -1, seq)
         ztr, rn = 0.0, 0.0
         for q in range(G):
-            arr, base = self.scal(me, 1, parity, q)
-            ztr += arr[base]
-            rn = max(rn, arr[base + 1])
+            base = 16 + q * 2
+            self.wait_elems(sh["msg_seq"][me], base, base + 2, seq)
+            ztr += sh["msg_val"][me][base]
+            rn = max(rn, sh["msg_val"][me][base + 1])
         done, beta = 0, 0.0
         if rn < self.tol:
             done = 1
@@ -127,7 +125,7 @@ class Rank(threading.Thread):
             if iters_old + 1 >= self.max_its:
                 done = 1
         self.pause()
-        # 5: K4 on the slice, stored into EVERY rank's p
+        # 5: K4 on the slice, stored into EVERY rank's p, then the "p slice ready" flag
         if not done:
             pn = self.z[lo:hi] + beta * self.p[lo:hi]
             for q in range(G):
@@ -142,6 +140,13 @@ class Rank(threading.Thread):
         if done:
             return
         self.wait(32, me, seq)
+
+    def wait_elems(self, seqarr, a, b, seq):
+        t0 = time.time()
+        while not np.all(seqarr[a:b] == seq):
+            if time.time() - t0 > 20:
+                raise TimeoutError(f"rank {self.me} waiting for elements [{a}, {b}) of sequence {seq}")
+            time.sleep(0)
 
     def run(self):
         try:
@@ -190,7 +195,9 @@ def test_sharded_x_protocol(G, n, m, iters, tol, jitter):
     b = rng.standard_normal(n)
     offs = [m * g // G for g in range(G + 1)]           # contiguous row blocks
     S = (n + G - 1) // G
-    shared = {"inbox": [np.zeros(G * S) for _ in range(G)], "p": [np.zeros(n) for _ in range(G)],
+    shared = {"inbox_val": [np.zeros(G * S) for _ in range(G)], "inbox_seq": [np.zeros(G * S, dtype=np.int64) for _ in range(G)],
+              "msg_val": [np.zeros(32) for _ in range(G)], "msg_seq": [np.zeros(32, dtype=np.int64) for _ in range(G)],
+              "p": [np.zeros(n) for _ in range(G)],
               "flags": [np.zeros(64, dtype=np.uint64) for _ in range(G)],
               "scal": [np.zeros(64) for _ in range(G)], "jitter": jitter}
     max_its = 10 * n

@@ -447,8 +447,8 @@ def main():
                                              "K3 on the slice": msv[7] * 1e3,
                                              "grid reduction + scalar exchange 2": msv[8] * 1e3,
                                              "K4 on the slice + p push": msv[9] * 1e3,
-                                             "release fence + ticket": msv[10] * 1e3,
-                                             "wait for the peers' p slices": msv[11] * 1e3}}
+                                             "unpack the peers' p slices (waits for elements in flight)": msv[10] * 1e3,
+                                             "ticket + control block": msv[11] * 1e3}}
             lib.scs_free_lin_sys_work(lw)
     if world == 1:
         dr = np.empty(n + m + 1)

@@ -215,6 +215,17 @@ __device__ __forceinline__ void ll_store(unsigned long long *dst2, double v, uns
   const unsigned long long w1 = (b >> 32) | ((unsigned long long)seq32 << 32);
   asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst2), "l"(w0), "l"(w1) : "memory");
 }
+// raw 16-byte read; ll_valid / ll_value interpret it (lets a caller issue several reads before it looks at any)
+__device__ __forceinline__ void ll_load_raw(const unsigned long long *src2, unsigned long long &w0,
+                                            unsigned long long &w1) {
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src2));
+}
+__device__ __forceinline__ bool ll_valid(unsigned long long w0, unsigned long long w1, unsigned seq32) {
+  return (unsigned)(w0 >> 32) == seq32 && (unsigned)(w1 >> 32) == seq32;
+}
+__device__ __forceinline__ double ll_value(unsigned long long w0, unsigned long long w1) {
+  return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+}
 // returns true and the value once both halves carry seq32
 __device__ __forceinline__ bool ll_try_load(const unsigned long long *src2, unsigned seq32, double &v) {
   unsigned long long w0, w1;

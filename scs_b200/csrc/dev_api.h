@@ -184,6 +184,7 @@ double *b200_p2p_base(int r);
 unsigned long long *b200_p2p_flags(int r);
 double *b200_p2p_pvec(int r);   /* rank r's p vector inside its exchange allocation (sharded-x mode) */
 double *b200_p2p_inbox(int r);  /* rank r's inbox [G][ceil(n/G)] of 16-byte elements (2 doubles of storage each) */
+double *b200_p2p_pbox(int r);   /* rank r's p-box: the peers' p slices arrive here as 16-byte elements, [n][2] */
 int b200_p2p_claim_pvec(void);  /* the exchange p vector serves one workspace at a time; 0 = claimed */
 void b200_p2p_release_pvec(void);
 unsigned long long b200_p2p_next_seq(void);

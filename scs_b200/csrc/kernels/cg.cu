@@ -490,21 +490,24 @@ k_cg_finish_p2p2(int n, double *__restrict__ y, P2pView pv, unsigned long long s
 //       2  collect the G partial scalars, add them in rank order => p'Gp and alpha, identical bits everywhere;
 //       3  K3 on the slice (x, r, z; z'r and ||r||_inf partials), pushed the same way;
 //       4  wait, combine => z'r, ||r||_inf, the stop decision and beta, identical everywhere;
-//       5  K4 on the slice: p = z + beta p, stored into EVERY rank's p (the all-gather is G-1 remote stores per
-//          element); the last block records the iteration in the control block and publishes "p slice ready";
-//       6  wait for the peers' p slices (the next K1 gathers from all of p).
-// No buffer needs double-buffering: a rank can enter iteration k+1 only after every peer has published its p slice
-// of iteration k, i.e. after every peer has finished reading its inbox and scalar slots of iteration k
-// (tests/test_shardx_protocol_cpu.py emulates the protocol with threads and random delays).
+//       5  K4 on the slice: p = z + beta p into the local p and, as self-validating elements, into every peer's p-box
+//          (the all-gather is G-1 remote 16-byte stores per element);
+//       6  unpack the peers' slices from my p-box into p, waiting per element (the next K1 gathers from all of p).
+// There is NO fence and NO flag anywhere in the protocol, and no buffer is double-buffered: a rank can overwrite a peer's
+// inbox / message slot / p-box element of iteration k only after it has consumed data that peer sent AFTER reading them
+// (rows of k+1 are sent after the peer's p slice of k arrived, which the peer sends after its reduction of k; messages
+// and p elements of k+1 are sent after the peer's rows / round-2 message of k+1 arrived): the data flow itself orders
+// the accesses (tests/test_shardx_protocol_cpu.py emulates the protocol with threads, split pushes and random delays).
 // Remote volume per rank and iteration: 2 (G-1)/G n doubles OUT; K3 / K4 shrink by G. All blocks spin on flags, so
 // the grid must be co-resident (<= #SMs blocks).
 // Exchange allocation (comm.cu): [0, 4n) buffers of the replicated modes, [4n, 5n) p, [5n, 7n+32) inbox
-// [G][S][2 words] with S = ceil(n / G), then the flag line (slots 32..39 "p slice") and 64 words of scalar messages
-// [round][from rank][4].
+// [G][S][2 words] with S = ceil(n / G), [7n+32, 9n+64) p-box [n][2 words], then the flag line (replicated modes only)
+// and 64 words of scalar messages [round][from rank][4].
 struct P2pViewX {
   int nranks, rank, S;
   const unsigned long long *inbox;  // local: element (q * S + i - lo) = rank q's partial for my element i (16 bytes)
-  double *peer_p[8];                // peer_p[q]: rank q's p vector as mapped here (peer_p[rank] == local p)
+  unsigned long long *peer_pbox[8];  // peer_pbox[q]: rank q's p-box as mapped here (element i = 2 words)
+  const unsigned long long *pbox;    // local p-box: the peers' slices of the new p arrive here
   unsigned long long *flags[8];
   unsigned long long *dbg;          // optional: 8 globaltimer stamps (ns) of block 0 at the phase boundaries, or NULL
 };
@@ -571,8 +574,21 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int y_has_px,
   // simply waited for -- the reduction overlaps the tail of the peers' K2), partial p'Gp
   double acc = 0.0;
   for (long long i = lo + gtid; i < hi; i += gstride) {
+    // all G reads are issued before any is looked at (they are independent); only a row that has not arrived is polled
+    unsigned long long w0[8], w1[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (q < G) ll_load_raw(pv.inbox + 2 * ((size_t)q * pv.S + (size_t)(i - lo)), w0[q], w1[q]);
     double sum = 0.0;
-    for (int q = 0; q < G; ++q) sum += ll_wait(pv.inbox + 2 * ((size_t)q * pv.S + (size_t)(i - lo)), seq32, ctl);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (q < G) {
+        const double vq = ll_valid(w0[q], w1[q], seq32)
+                              ? ll_value(w0[q], w1[q])
+                              : ll_wait(pv.inbox + 2 * ((size_t)q * pv.S + (size_t)(i - lo)), seq32, ctl);
+        sum += vq;  // rank order
+      }
+    }
     const double base = y_has_px ? Gp[i] + sum : sum;
     const double pi = p[i];
     const double out = fma(rx[i], pi, base);
@@ -653,17 +669,31 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int y_has_px,
   const double ztr_new = s_bc[0], rnorm = s_bc[1], beta = s_bc[2];
   const int done = s_bc[3] != 0.0;
 
-  // ---- 5: K4 on the slice, pushed into every rank's p (skipped once the stop test fired, like k_cg_pupdate)
+  // ---- 5: K4 on the slice (skipped once the stop test fired, like k_cg_pupdate): the new p goes into the local p and,
+  // as self-validating elements, into every peer's p-box (the all-gather is G-1 remote 16-byte stores per element)
   if (!done) {
     for (long long i = lo + gtid; i < hi; i += gstride) {
       const double pn = fma(beta, p[i], z[i]);
-      for (int q = 0; q < G; ++q) pv.peer_p[q][i] = pn;  // q == me: the local p
+      p[i] = pn;
+      for (int q = 0; q < G; ++q)
+        if (q != me) ll_store(pv.peer_pbox[q] + 2 * (size_t)i, pn, seq32);
     }
   }
-  __syncthreads();
   px_stamp(pv, 5);
+  // ---- 6: unpack the peers' slices from my p-box into p, waiting per element for what is still in flight (the next K1
+  // gathers from all of p). No fence, no flag: the elements validate themselves.
+  if (!done) {
+    for (int q = 0; q < G; ++q) {
+      if (q == me) continue;
+      const long long qlo = (long long)n * q / G, qhi = (long long)n * (q + 1) / G;
+      for (long long i = qlo + gtid; i < qhi; i += gstride) p[i] = ll_wait(pv.pbox + 2 * (size_t)i, seq32, ctl);
+    }
+  }
+  px_stamp(pv, 6);
+  __syncthreads();
   if (threadIdx.x == 0) {
-    asm volatile("fence.acq_rel.sys;" ::: "memory");  // release: this block's p stores before its ticket
+    // the last block to arrive records the iteration in the control block: every block read its start values long ago
+    __threadfence();
     if (atomicAdd(&counters[6], 1u) == gridDim.x - 1) {
       counters[6] = 0u;
       ctl->ztr_prev = ztr_old;
@@ -674,15 +704,9 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int y_has_px,
       ctl->iters = iters_old + 1;
       if (!done) ctl->beta = beta;
       if (done) ctl->done = 1;
-      asm volatile("fence.acq_rel.sys;" ::: "memory");
-      for (int q = 0; q < G; ++q) *((volatile unsigned long long *)(pv.flags[q] + 32 + me)) = seq;
     }
-    px_stamp(pv, 6);
-    // ---- 6: the peers' slices of the new p have landed in my p
-    if (!done) px_wait(myflags, 32, G, me, seq, ctl);
     px_stamp(pv, 7);
   }
-  __syncthreads();
 }
 
 __global__ void k_add_if_not(int n, double *__restrict__ a, const double *__restrict__ b, const int *skip) {
@@ -886,8 +910,9 @@ static int cg_iteration_shard_x(B200Cg *cg, double *d_x, cudaEvent_t *ev = nullp
   P2pViewX pv;
   pv.nranks = G; pv.rank = me; pv.S = (cg->n + G - 1) / G;
   pv.inbox = (const unsigned long long *)b200_p2p_inbox(me);
+  pv.pbox = (const unsigned long long *)b200_p2p_pbox(me);
   for (int r = 0; r < 8; ++r) {
-    pv.peer_p[r] = r < G ? b200_p2p_pvec(r) : nullptr;
+    pv.peer_pbox[r] = r < G ? (unsigned long long *)b200_p2p_pbox(r) : nullptr;
     pv.flags[r] = r < G ? b200_p2p_flags(r) : nullptr;
   }
   pv.dbg = ev ? reinterpret_cast<unsigned long long *>(cg->d_partials + 3 * 2048) : nullptr;  // timing runs only

@@ -145,9 +145,11 @@ extern "C" unsigned long long b200_p2p_next_seq(void) { return ++g_p2p_seq; }
 // offsets (in doubles) inside a rank's exchange allocation of stride n
 #define P2P_OFF_P(n) ((size_t)4 * (n))          /* p vector of the sharded-x mode */
 #define P2P_OFF_INBOX(n) ((size_t)5 * (n))      /* inbox [G][ceil(n/G)] of 16-byte self-validating elements */
-#define P2P_OFF_FLAGS(n) ((size_t)7 * (n) + 32) /* 64 flags, then 64 scalar-message words */
+#define P2P_OFF_PBOX(n) ((size_t)7 * (n) + 32)  /* the peers' slices of p as 16-byte self-validating elements, [n][2] */
+#define P2P_OFF_FLAGS(n) ((size_t)9 * (n) + 64) /* 64 flags, then 64 scalar-message words */
 extern "C" double *b200_p2p_pvec(int r) { return g_p2p.base[r] + P2P_OFF_P(g_p2p.n); }
 extern "C" double *b200_p2p_inbox(int r) { return g_p2p.base[r] + P2P_OFF_INBOX(g_p2p.n); }
+extern "C" double *b200_p2p_pbox(int r) { return g_p2p.base[r] + P2P_OFF_PBOX(g_p2p.n); }
 
 // the exchange p vector can serve ONE workspace at a time (sharded-x mode): claim / release
 static int g_p2p_p_claimed = 0;
@@ -163,7 +165,7 @@ extern "C" int b200_p2p_setup(int n_req) {
   if (g_p2p.ok && g_p2p.n >= n_req) return 0;
   if (g_p2p.ok) return -1;  // one allocation per process, sized generously below; larger systems use NCCL
   // stride of the allocation: at least 2^23 doubles, so that the workspaces of different sizes a process creates one
-  // after the other (tests, bench.py) share it; 7 x 64 MB = 448 MB of the 180 GB
+  // after the other (tests, bench.py) share it; 9 x 64 MB = 600 MB of the 180 GB
   const int n = n_req > (1 << 23) ? n_req : (1 << 23);
   // Every rank reaches the two collectives below whatever happens locally (an early return on one
   // rank -- SCS_B200_P2P=0 set for it alone, a failed allocation -- would leave the others blocked in NCCL):

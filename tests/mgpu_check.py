@@ -106,7 +106,7 @@ if os.environ.get("MGPU_TIME", "1") != "0":
                   f"K2 local partial + push + signal {float(tmx[1])*1e3:.1f} | slice kernel (reduce, 2 scalar exchanges, K3/K4, "
                   f"p push, waits) {float(tmx[2])*1e3:.1f} | iteration with events {float(tmx[3])*1e3:.1f}", flush=True)
             names = ("reduce slice (waits for rows in flight)", "slice dot: grid reduction + scalar exchange 1", "K3 on the slice",
-                     "grid reduction + scalar exchange 2", "K4 on the slice + p push", "release fence + ticket", "wait for the peers' p slices")
+                     "grid reduction + scalar exchange 2", "K4 on the slice + p push", "unpack the peers' p slices (waits for elements in flight)", "ticket + control block")
             print(f"[C2 sharded over {world} GPUs] inside the slice kernel, rank 0 block 0, last iteration (us): " +
                   " | ".join(f"{nm} {msv[5 + k]*1e3:.1f}" for k, nm in enumerate(names)), flush=True)
         rng2 = np.random.default_rng(99)

@@ -4,7 +4,7 @@ thread; the exchange allocations (inbox [G][S], the p vector), flag lines and sc
 out like the device buffers. Data moves only by STORES into the peer's arrays, exactly as on the device: the K2 SpMV
 pushes each output row into the owner's inbox as a SELF-VALIDATING element (value + the sequence number of the exchange,
 common.cuh ll_store: no "partial ready" flag exists, the reader waits per element), the partial scalars travel the same
-way, K4 stores the new p slice into every rank's p followed by the only flag of the protocol (slot 32 + rank). The
+way, and so do the new p slices (into the peers' p-boxes, unpacked by the receiver): no flag and no fence anywhere. The
 emulation follows the kernel phase by phase -- same rank-order sums, same stop logic, NO double buffering of inbox,
 messages or p, writes of one push deliberately split in two halves with a delay between them -- and checks: no deadlock, no torn reads under random delays (ranks run up to an iteration apart), all
 ranks hold bit-identical p / alpha / beta / stop decisions, and the iterates agree with a plain single-process
@@ -125,21 +125,29 @@ class Rank(threading.Thread):
             if iters_old + 1 >= self.max_its:
                 done = 1
         self.pause()
-        # 5: K4 on the slice, stored into EVERY rank's p, then the "p slice ready" flag
+        # 5: K4 on the slice: into the local p and, as (value, seq) elements, into every peer's p-box (two halves)
         if not done:
             pn = self.z[lo:hi] + beta * self.p[lo:hi]
-            for q in range(G):
-                sh["p"][q][lo:hi] = pn
+            self.p[lo:hi] = pn
+            mid = (hi - lo) // 2
+            for a, b in ((0, mid), (mid, hi - lo)):
+                for q in range(G):
+                    if q != me:
+                        sh["pbox_val"][q][lo + a:lo + b] = pn[a:b]
+                        sh["pbox_seq"][q][lo + a:lo + b] = seq
+                self.pause()
         self.ctl.update(ztr=ztr, rnorm=rn, iters=iters_old + 1, alpha=alpha, beta=beta if not done else self.ctl["beta"],
                         done=done)
-        for q in range(G):
-            sh["flags"][q][32 + me] = seq
         self.history.append((alpha, beta, ztr, rn, done))
-        self.pause()
-        # 6: the peers' slices of the new p have landed
+        # 6: unpack the peers' slices from my p-box, waiting per element
         if done:
             return
-        self.wait(32, me, seq)
+        for q in range(G):
+            if q == me:
+                continue
+            qlo, qhi = n * q // G, n * (q + 1) // G
+            self.wait_elems(sh["pbox_seq"][me], qlo, qhi, seq)
+            self.p[qlo:qhi] = sh["pbox_val"][me][qlo:qhi]
 
     def wait_elems(self, seqarr, a, b, seq):
         t0 = time.time()
@@ -198,6 +206,7 @@ def test_sharded_x_protocol(G, n, m, iters, tol, jitter):
     shared = {"inbox_val": [np.zeros(G * S) for _ in range(G)], "inbox_seq": [np.zeros(G * S, dtype=np.int64) for _ in range(G)],
               "msg_val": [np.zeros(32) for _ in range(G)], "msg_seq": [np.zeros(32, dtype=np.int64) for _ in range(G)],
               "p": [np.zeros(n) for _ in range(G)],
+              "pbox_val": [np.zeros(n) for _ in range(G)], "pbox_seq": [np.zeros(n, dtype=np.int64) for _ in range(G)],
               "flags": [np.zeros(64, dtype=np.uint64) for _ in range(G)],
               "scal": [np.zeros(64) for _ in range(G)], "jitter": jitter}
     max_its = 10 * n

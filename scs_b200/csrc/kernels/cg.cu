@@ -597,13 +597,19 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int y_has_px,
   }
   px_stamp(pv, 1);
   {
-    // slice total by the deterministic parallel last-block reduction (common.cuh grid_finish: fixed slots, fixed tree),
-    // then one self-validating message to every rank (no fence, no flag)
+    // slice total: every block publishes its partial as a self-validating element (local memory), block 0 collects
+    // them in a fixed order (slot t -> thread t, then the fixed block_sum tree) and sends ONE message to every rank --
+    // no atomic ticket, no fence, no last-block serialisation on the critical path
     double a[1] = {acc};
     block_sum<1>(a, s_red);
-    if (grid_finish<1>(a, partials, &counters[4], 0u, s_red)) {
+    unsigned long long *slots = reinterpret_cast<unsigned long long *>(partials);
+    if (threadIdx.x == 0) ll_store(slots + 2 * blockIdx.x, a[0], seq32);
+    if (blockIdx.x == 0) {
+      double t[1] = {0.0};
+      for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) t[0] += ll_wait(slots + 2 * b, seq32, ctl);
+      block_sum<1>(t, s_red);
       if (threadIdx.x == 0)
-        for (int q = 0; q < G; ++q) ll_store(px_msg(pv, q, 0, me), a[0], seq32);
+        for (int q = 0; q < G; ++q) ll_store(px_msg(pv, q, 0, me), t[0], seq32);
     }
     if (threadIdx.x == 0) {
       // ---- 2: all partial scalars -> alpha (rank order: identical bits on every rank)
@@ -635,12 +641,23 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int y_has_px,
     double sm[1] = {acc0}, mx[1] = {acc1};
     block_sum<1>(sm, s_red);
     block_max<1>(mx, s_red + 64);
-    double both[2] = {sm[0], mx[0]};
-    if (grid_finish<2>(both, partials + 2048, &counters[5], 2u, s_red)) {
+    unsigned long long *slots = reinterpret_cast<unsigned long long *>(partials + 1024);
+    if (threadIdx.x == 0) {
+      ll_store(slots + 4 * blockIdx.x, sm[0], seq32);
+      ll_store(slots + 4 * blockIdx.x + 2, mx[0], seq32);
+    }
+    if (blockIdx.x == 0) {
+      double t[1] = {0.0}, u[1] = {0.0};
+      for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+        t[0] += ll_wait(slots + 4 * b, seq32, ctl);
+        u[0] = fmax(u[0], ll_wait(slots + 4 * b + 2, seq32, ctl));
+      }
+      block_sum<1>(t, s_red);
+      block_max<1>(u, s_red + 64);
       if (threadIdx.x == 0)
         for (int q = 0; q < G; ++q) {
-          ll_store(px_msg(pv, q, 1, me), both[0], seq32);
-          ll_store(px_msg(pv, q, 1, me) + 2, both[1], seq32);
+          ll_store(px_msg(pv, q, 1, me), t[0], seq32);
+          ll_store(px_msg(pv, q, 1, me) + 2, u[0], seq32);
         }
     }
     if (threadIdx.x == 0) {

@@ -602,7 +602,7 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int y_has_px,
     // no atomic ticket, no fence, no last-block serialisation on the critical path
     double a[1] = {acc};
     block_sum<1>(a, s_red);
-    unsigned long long *slots = reinterpret_cast<unsigned long long *>(partials);
+    unsigned long long *slots = reinterpret_cast<unsigned long long *>(partials + 2048);  // [2048, 4096): only this kernel
     if (threadIdx.x == 0) ll_store(slots + 2 * blockIdx.x, a[0], seq32);
     if (blockIdx.x == 0) {
       double t[1] = {0.0};
@@ -641,7 +641,7 @@ k_cgx_iteration(int n, P2pViewX pv, unsigned long long seq, int y_has_px,
     double sm[1] = {acc0}, mx[1] = {acc1};
     block_sum<1>(sm, s_red);
     block_max<1>(mx, s_red + 64);
-    unsigned long long *slots = reinterpret_cast<unsigned long long *>(partials + 1024);
+    unsigned long long *slots = reinterpret_cast<unsigned long long *>(partials + 3072);
     if (threadIdx.x == 0) {
       ll_store(slots + 4 * blockIdx.x, sm[0], seq32);
       ll_store(slots + 4 * blockIdx.x + 2, mx[0], seq32);

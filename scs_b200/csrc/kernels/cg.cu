@@ -475,7 +475,8 @@ k_cg_finish_p2p2(int n, double *__restrict__ y, P2pView pv, unsigned long long s
 
 
 // ---------------------------------------------------------------------------------------------
-// "Sharded-x" CG iteration for G >= 2 ranks, PUSH-based (SCS_B200_SHARD_X=1 / scs_b200_set_shard_x(1)).
+// "Sharded-x" CG iteration for G >= 2 ranks, PUSH-based (the default multi-GPU mode; SCS_B200_SHARD_X=0 /
+// scs_b200_set_shard_x(0) select the replicated modes above).
 // p stays replicated (it is the SpMV gather vector) but lives in the peer-mapped exchange allocation; x, r, z and
 // Gp are owned by n-slices [n g/G, n (g+1)/G). Data only ever moves by STORES into peer memory (NVLink writes
 // pipeline; remote loads pay the full round trip), synchronisation is by sequence-numbered flags:
@@ -887,13 +888,14 @@ static int mat_vec(B200Cg *cg, const double *d_x, double *d_y, int with_dot, con
   return b200_spmv(At, &a);
 }
 
-// sharded-x push mode (see k_cgx_iteration): -1 = read SCS_B200_SHARD_X once, 0 = off, 1 = on
+// sharded-x push mode (see k_cgx_iteration): -1 = read SCS_B200_SHARD_X once (default ON since its hardware runs at 2
+// and 4 GPUs, profiles/README.md "multi-GPU"; =0 selects the replicated modes), 0 = off, 1 = on
 static int g_shard_x = -1;
 extern "C" void scs_b200_set_shard_x(int on) { g_shard_x = on ? 1 : 0; }
 static int shard_x_active(const B200Cg *cg) {
   if (g_shard_x < 0) {
     const char *e = getenv("SCS_B200_SHARD_X");
-    g_shard_x = (e && atoi(e) != 0) ? 1 : 0;
+    g_shard_x = (e && atoi(e) == 0) ? 0 : 1;
   }
   return g_shard_x == 1 && cg->nranks > 1 && cg->use_p2p && cg->d_p2p_route != nullptr;
 }

@@ -76,6 +76,8 @@ if os.environ.get("MGPU_TIME", "1") != "0":
     w = lib.scs_init_lin_sys_work(C.byref(hp.A), None, capi.dptr(dr))
     ab = C.c_double()
     lib.scs_b200_set_p2p_mode.argtypes = [C.c_int]
+    lib.scs_b200_set_shard_x.argtypes = [C.c_int]
+    lib.scs_b200_set_shard_x(0)          # the replicated modes first (sharded-x is the default)
     for mode, label in ((1, "one pass: every rank reads every partial"), (2, "two-phase: reduce-scatter + all-gather")):
         lib.scs_b200_set_p2p_mode(mode)
         ms = lib.scs_b200_time_cg_iter(w, 30, C.byref(ab))
@@ -84,9 +86,8 @@ if os.environ.get("MGPU_TIME", "1") != "0":
         if rank == 0:
             print(f"[C2 sharded over {world} GPUs] CG iteration, {label}: {float(t[0])*1e3:.1f} us", flush=True)
     lib.scs_b200_set_p2p_mode(0)
-    if os.environ.get("MGPU_SHARD_X"):
+    if os.environ.get("MGPU_SHARD_X", "1") != "0":
         # push-based sharded-x mode (kernels/cg.cu k_cgx_iteration): time it, then check a solve
-        lib.scs_b200_set_shard_x.argtypes = [C.c_int]
         lib.scs_b200_set_shard_x(1)
         ms = lib.scs_b200_time_cg_iter(w, 30, C.byref(ab))
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -116,6 +117,7 @@ if os.environ.get("MGPU_TIME", "1") != "0":
         lib.scs_b200_set_shard_x(0)
         base = rhs.copy()
         assert lib.scs_solve_lin_sys(w, capi.dptr(base), None, 1e-10) == 0
+        lib.scs_b200_set_shard_x(1)
         rel = np.abs(mine - base).max() / np.abs(base).max()
         if rank == 0:
             print(f"[C2 sharded over {world} GPUs] KKT solve, sharded-x vs default sharded mode: rel diff {rel:.2e} "

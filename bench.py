@@ -29,7 +29,8 @@ eps = 0 (so exactly K iterations run) -- identical algorithmic work, identical `
 
 --impl reference times that same reference solver for the same K cold iterations as the whole arm.
 N > 1: one process per GPU, ONE cooperative solve of the same workload (strong scaling): A is row-sharded across the
-ranks; per CG iteration the partial products are summed by a fused kernel over NVLink peer memory.
+ranks; the CG runs in the sharded-x push mode over NVLink peer memory and the line carries the
+per-phase timeline of one CG iteration (`cg_phases_us`, max over ranks).
 """
 import argparse
 import ctypes as C

@@ -263,6 +263,10 @@ void scs_b200_free_data(ScsData *d, ScsCone *k, ScsSettings *stgs);
 long long scs_b200_launch_count(void);
 /* 1 if a CUDA device of compute capability 10.x is usable, else 0. */
 scs_int scs_b200_device_ok(void);
+/* Device memory is cached across workspaces (a freed block is handed to the next allocation of the same size instead of
+ * going back to the driver: cudaMalloc / cudaFree cost milliseconds each and cudaFree synchronises the device). This
+ * returns every cached block to the driver; SCS_B200_POOL=0 disables the caching altogether. */
+void scs_b200_release_memory(void);
 
 #ifdef __cplusplus
 }

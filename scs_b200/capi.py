@@ -258,6 +258,7 @@ def _declare(lib, ours):
     lib.scs_b200_row_partition.argtypes = [C.c_int, C.c_int, c_int_p, c_int_p, C.c_int, c_int_p]
     lib.scs_b200_launch_count.restype = C.c_longlong
     lib.scs_b200_device_ok.restype = C.c_int
+    lib.scs_b200_release_memory.restype = None
 
 
 _lib = None

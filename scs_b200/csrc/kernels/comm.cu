@@ -177,7 +177,10 @@ extern "C" int b200_p2p_setup(int n_req) {
   if (!N_AllGather) return -1;  // same library on every rank: a uniform outcome
   cudaStream_t st = (cudaStream_t)b200_stream();
   const size_t bytes = (P2P_OFF_FLAGS(n) + 64 + 64) * 8;
-  double *mine = can_try ? (double *)b200_malloc(bytes) : nullptr;
+  // straight from the driver, not from the caching allocator: the block is exported to the peers through CUDA IPC and
+  // must not be recycled for anything else while they may have it mapped
+  double *mine = nullptr;
+  if (can_try && cudaMalloc((void **)&mine, bytes) != cudaSuccess) { cudaGetLastError(); mine = nullptr; }
   cudaIpcMemHandle_t h;
   memset(&h, 0, sizeof(h));
   if (!mine || b200_memset0(mine, bytes) != 0) can_try = 0;
@@ -222,7 +225,7 @@ extern "C" int b200_p2p_setup(int n_req) {
   }
   if (!g_p2p.ok) {
     for (void *p : opened) cudaIpcCloseMemHandle(p);
-    b200_free(mine);
+    if (mine) cudaFree(mine);
     memset(&g_p2p, 0, sizeof(g_p2p));
     fprintf(stderr, "scs_b200: peer-memory (CUDA IPC) mapping unavailable, using NCCL all-reduce\n");
   }
@@ -235,7 +238,7 @@ static void p2p_teardown(void) {
   b200_sync();
   for (int r = 0; r < g_nranks && r < P2P_MAX_RANKS; ++r) {
     if (!g_p2p.base[r]) continue;
-    if (r == g_rank) b200_free(g_p2p.base[r]);
+    if (r == g_rank) cudaFree(g_p2p.base[r]);
     else cudaIpcCloseMemHandle(g_p2p.base[r]);
   }
   memset(&g_p2p, 0, sizeof(g_p2p));

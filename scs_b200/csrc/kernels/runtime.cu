@@ -75,20 +75,91 @@ extern "C" int b200_device_ok(void) { return b200_runtime_init() == 0; }
 extern "C" int b200_num_sms(void) { return g_num_sms; }
 extern "C" void *b200_stream(void) { return (void *)g_stream; }
 
+// ---------------------------------------------------------------------------------------------
+// Device memory: a small caching allocator. cudaMalloc / cudaFree cost milliseconds per call for the large buffers of
+// a workspace (and cudaFree synchronises the device); a process that solves one problem after another -- the common
+// production pattern, and bench.py's end-to-end call -- gets the blocks of the previous workspace back instead.
+// Freed blocks are kept in a size-keyed list (exact size match on reuse: workspaces of one problem shape reuse each
+// other's blocks) up to B200_POOL_MAX_BYTES; beyond that, and under memory pressure (a failed cudaMalloc trims the
+// pool and retries), blocks go back to the driver. SCS_B200_POOL=0 disables caching; scs_b200_release_memory() trims.
+// Reused blocks are NOT zeroed -- like fresh cudaMalloc memory, whose contents are unspecified too.
+#include <map>
+#include <vector>
+static std::mutex g_pool_mu;
+static std::multimap<size_t, void *> g_pool_free;  // size -> block
+static std::map<void *, size_t> g_pool_size;       // every live or cached block we handed out -> its size
+static size_t g_pool_cached = 0;
+static int g_pool_on = -1;
+#define B200_POOL_MAX_BYTES ((size_t)24 << 30)
+static bool pool_enabled() {
+  if (g_pool_on < 0) {
+    const char *e = getenv("SCS_B200_POOL");
+    g_pool_on = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return g_pool_on == 1;
+}
+static void pool_trim_locked() {
+  for (auto &kv : g_pool_free) {
+    cudaFree(kv.second);
+    g_pool_size.erase(kv.second);
+  }
+  g_pool_free.clear();
+  g_pool_cached = 0;
+}
+extern "C" void scs_b200_release_memory(void) {
+  if (g_init != 1) return;
+  bind_thread();
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  cudaStreamSynchronize(g_stream);
+  pool_trim_locked();
+}
+
 extern "C" void *b200_malloc(size_t bytes) {
   if (b200_runtime_init() != 0) return nullptr;
   void *p = nullptr;
   if (bytes == 0) bytes = 16;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (pool_enabled()) {
+    auto it = g_pool_free.find(bytes);
+    if (it != g_pool_free.end()) {
+      p = it->second;
+      g_pool_free.erase(it);
+      g_pool_cached -= bytes;
+      return p;
+    }
+  }
   cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess && g_pool_cached > 0) {  // memory pressure: give the cached blocks back and retry once
+    cudaGetLastError();
+    cudaStreamSynchronize(g_stream);
+    pool_trim_locked();
+    e = cudaMalloc(&p, bytes);
+  }
   if (e != cudaSuccess) {
     b200_set_error("cudaMalloc", e, __FILE__, __LINE__);
     return nullptr;
   }
+  g_pool_size[p] = bytes;
   return p;
 }
 extern "C" void b200_free(void *p) {
   if (!p) return;
   bind_thread();
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  auto it = g_pool_size.find(p);
+  if (it == g_pool_size.end()) {  // not ours (cannot happen): hand it to the driver
+    cudaFree(p);
+    return;
+  }
+  const size_t bytes = it->second;
+  if (pool_enabled() && g_pool_cached + bytes <= B200_POOL_MAX_BYTES) {
+    // the block may still be in use by work enqueued on the library stream: every consumer of pooled memory is
+    // ordered on that same stream, so handing it to the next b200_malloc is safe without a synchronisation
+    g_pool_free.insert({bytes, p});
+    g_pool_cached += bytes;
+    return;
+  }
+  g_pool_size.erase(it);
   cudaFree(p);
 }
 extern "C" void *b200_host_alloc(size_t bytes) {

@@ -353,9 +353,13 @@ def main():
     barrier()
     t0 = time.time()
     w, info_e, sols = run_solver(lib, capi, hp, dict(max_iters=args.steps, **eps0))
+    t_fin = time.time()
     lib.scs_finish(w)
     torch.cuda.synchronize()
     e2e_s = time.time() - t0
+    e2e_parts = {"init_ms": info_e.setup_time, "solve_ms": info_e.solve_time,
+                 "finish_ms": 1e3 * (time.time() - t_fin),
+                 "other_ms (ctypes, result copies)": 1e3 * e2e_s - info_e.setup_time - info_e.solve_time - 1e3 * (time.time() - t_fin)}
     h2d = nnz * 12 + (n + 1) * 4 + (m + n) * 8          # A (vals+idx+ptr), b, c
     d2h = (n + 2 * m) * 8                                # x, y, s
 
@@ -530,7 +534,7 @@ def main():
              "replicated x-space: a fused kernel sums the peers' partials in rank order") +
             "; cones, AA and the l-vectors replicated",
             "e2e": {"value": e2e_value, "unit": "iters/s", "h2d_bytes_per_step": h2d / args.steps,
-                    "d2h_bytes_per_step": d2h / args.steps,
+                    "d2h_bytes_per_step": d2h / args.steps, "breakdown": e2e_parts,
                     "note": "whole scs() on host buffers: scs_init (transpose + SpMV plans, H2D, device equilibration) + K cold iterations + D2H; one untimed 3-iteration call ran before (process cold start)"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),

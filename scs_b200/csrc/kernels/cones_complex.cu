@@ -161,7 +161,7 @@ extern "C" void b200_cpsd_destroy(B200CpsdCones *c) {
     b200_free(g.d_work); free(g.h_work);
   }
   if (c->params) cusolverDnDestroyParams(c->params);
-  if (c->solver) cusolverDnDestroy(c->solver);
+  b200_solver_release((void *)c->solver);
   delete c;
 }
 
@@ -178,9 +178,8 @@ extern "C" B200CpsdCones *b200_cpsd_create(int cssize, const int *h_cs, long lon
     off += (long long)h_cs[i] * h_cs[i];
   }
   if (by_k.empty()) return c;
-  if (cusolverDnCreate(&c->solver) != CUSOLVER_STATUS_SUCCESS ||
-      cusolverDnSetStream(c->solver, (cudaStream_t)b200_stream()) != CUSOLVER_STATUS_SUCCESS ||
-      cusolverDnCreateParams(&c->params) != CUSOLVER_STATUS_SUCCESS) {
+  c->solver = (cusolverDnHandle_t)b200_solver_acquire();
+  if (!c->solver || cusolverDnCreateParams(&c->params) != CUSOLVER_STATUS_SUCCESS) {
     b200_cpsd_destroy(c);
     return nullptr;
   }

@@ -1198,21 +1198,34 @@ __global__ void k_stored_len(int nrows, const int *__restrict__ rp, int *__restr
 __global__ void k_fill_flagged(int nrows, const int *__restrict__ rp, const int *__restrict__ sp,
                                const int *__restrict__ ci, const double *__restrict__ va, int *__restrict__ oi,
                                double *__restrict__ ov) {
-  // one warp per row group: rows are short (<= SPMV3_MAXROW); lane-strided copy of each row
+  // one lane per row; a row longer than SPMV3_MAXROW gets an END at the end of every balanced piece (the "virtual
+  // rows" of Spmv3Plan::vptr: the first len % pieces pieces hold one entry more) -- same cut as spmv3_build_plan
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int r0 = warp * 32; r0 < nrows; r0 += nwarps * 32) {
     const int r = r0 + lane;
     if (r < nrows) {
-      const int a = rp[r], b = rp[r + 1];
+      const int a = rp[r], b = rp[r + 1], len = b - a;
       int pos = sp[r];
       if (a == b) {
         oi[pos] = (int)(SPMV3_END | SPMV3_SKIP);
         ov[pos] = 0.0;
-      } else {
+      } else if (len <= SPMV3_MAXROW) {
         for (int k = a; k < b; ++k, ++pos) {
           oi[pos] = (k == b - 1) ? (int)((unsigned)ci[k] | SPMV3_END) : ci[k];
           ov[pos] = va[k];
+        }
+      } else {
+        const int pieces = (len + SPMV3_MAXROW - 1) / SPMV3_MAXROW, small = len / pieces, big = len % pieces;
+        int left = small + (big > 0 ? 1 : 0), q = 0;
+        for (int k = a; k < b; ++k, ++pos) {
+          const bool end = --left == 0;
+          oi[pos] = end ? (int)((unsigned)ci[k] | SPMV3_END) : ci[k];
+          ov[pos] = va[k];
+          if (end) {
+            ++q;
+            left = small + (q < big ? 1 : 0);
+          }
         }
       }
     }
@@ -1253,7 +1266,10 @@ extern "C" B200Spmv *b200_spmv_create_dev(int nrows, int ncols, long long nnz, c
     ok = ok && b200_d2h(h_sp.data(), M->d_rowptr, (size_t)(nrows + 1) * 4) == 0 && b200_sync() == 0;
     b200_count_launch(2);
   }
-  if (ok && h_max > SPMV3_MAXROW) ok = false;  // virtual rows: host builder
+  {
+    const char *lr = getenv("SCS_B200_SPMV_LONGROWS");
+    if (ok && h_max > SPMV3_MAXROW && lr && atoi(lr) == 0) ok = false;  // long rows disabled: host builder (v2)
+  }
   if (ok) {
     stored = h_sp[(size_t)nrows];
     if (stored < 0) ok = false;
@@ -1275,9 +1291,52 @@ extern "C" B200Spmv *b200_spmv_create_dev(int nrows, int ncols, long long nnz, c
     int cap = SPMV3_CTAS_PER_SM * b200_num_sms();
     const char *gq = getenv("SCS_B200_SPMV_GRID");
     if (gq && atoi(gq) > 0 && atoi(gq) < cap) cap = atoi(gq);
-    P.nvrows = nrows;
-    spmv3_tiles_from_rowptr(nrows, h_sp.data(), stored, cap, P);  // overlaps the fill kernel
-    M->grid = P.grid; M->ntiles = P.nwt; M->tile_nnz = SPMV3_WT; M->nvrows = nrows;
+    // virtual row pointers (sequential O(rows) host pass, overlaps the fill kernel): identical to the stored row
+    // pointers unless a row is longer than a warp-tile -- then its pieces, cut exactly as k_fill_flagged cuts them
+    std::vector<int> vrp_store;
+    const int *vrp = h_sp.data();
+    int nv = nrows;
+    if (h_max > SPMV3_MAXROW) {
+      long long extra = 0;
+      for (int r = 0; r < nrows; ++r) {
+        const int len = h_sp[(size_t)r + 1] - h_sp[r];
+        if (len > SPMV3_MAXROW) extra += (len + SPMV3_MAXROW - 1) / SPMV3_MAXROW - 1;
+      }
+      if ((long long)nrows + extra >= (1LL << 30)) ok = false;
+      if (ok) {
+        nv = (int)(nrows + extra);
+        vrp_store.resize((size_t)nv + 1);
+        P.vptr.resize((size_t)nrows + 1);
+        int v = 0;
+        for (int r = 0; r < nrows; ++r) {
+          P.vptr[r] = v;
+          const int len = h_sp[(size_t)r + 1] - h_sp[r];
+          if (len > SPMV3_MAXROW) {
+            const int pieces = (len + SPMV3_MAXROW - 1) / SPMV3_MAXROW, small = len / pieces, big = len % pieces;
+            int e = h_sp[r];
+            for (int q = 0; q < pieces; ++q) {
+              vrp_store[v++] = e;
+              e += small + (q < big ? 1 : 0);
+            }
+          } else {
+            vrp_store[v++] = h_sp[r];
+          }
+        }
+        P.vptr[nrows] = v;
+        vrp_store[v] = h_sp[(size_t)nrows];
+        vrp = vrp_store.data();
+      }
+    }
+    P.nvrows = nv;
+    if (ok) spmv3_tiles_from_rowptr(nv, vrp, stored, cap, P);
+    M->grid = P.grid; M->ntiles = P.nwt; M->tile_nnz = SPMV3_WT; M->nvrows = nv;
+    if (ok && !P.vptr.empty()) {
+      M->d_vptr = (int *)b200_malloc(P.vptr.size() * 4);
+      M->d_vscratch = (double *)b200_malloc((size_t)nv * 8);
+      ok = M->d_vptr && M->d_vscratch && b200_h2d(M->d_vptr, P.vptr.data(), P.vptr.size() * 4) == 0;
+    }
+  }
+  if (ok) {
     M->d_wt3 = (int4 *)b200_malloc(P.wt.size() * sizeof(int4));
     M->d_cta_begin3 = (int *)b200_malloc(P.cta_begin.size() * 4);
     M->d_partials = (double *)b200_malloc((size_t)B200_MAX_PARTIALS * 8);

@@ -132,6 +132,36 @@ def test_spmv_flagged_stream_ragged(lib, reflib, m, n, mean_nnz, seed, grid_cap,
         lib.scs_free_lin_sys_work(w)
 
 
+@pytest.mark.parametrize("m,n,col_nnz,seed", [(3000, 50, 700, 4), (64, 5000, 40, 5), (30000, 10000, 10, 3)])
+def test_device_built_operators_equal_host_built(lib, m, n, col_nnz, seed, monkeypatch):
+    """scs_init_lin_sys_work builds both flagged streams on the device (kernels/setup.cu; rows longer than a warp-tile
+    are cut into the same balanced pieces as the host plan builder cuts them) -- the result must be BIT-identical to
+    the host builders' (SCS_B200_HOST_SETUP=1): same stream, same warp-tiles, same summation order."""
+    rng = np.random.default_rng(seed)
+    A = problems.random_sparse_csc(m, n, col_nnz, rng)
+    hp = capi.HostProblem(A, np.zeros(m), np.zeros(n), {"l": m})
+    dr = diag_r_for(n, m, 0)
+    x, yv, rhs = rng.standard_normal(n), rng.standard_normal(m), rng.standard_normal(n + m)
+    outs = []
+    for host in (0, 1):
+        if host:
+            monkeypatch.setenv("SCS_B200_HOST_SETUP", "1")
+        else:
+            monkeypatch.delenv("SCS_B200_HOST_SETUP", raising=False)
+        w = lib.scs_init_lin_sys_work(C.byref(hp.A), None, capi.dptr(dr))
+        assert w
+        try:
+            ax, aty, sol = np.zeros(m), np.zeros(n), rhs.copy()
+            assert lib.scs_b200_accum_by_a(w, capi.dptr(x), capi.dptr(ax), 0) == 0
+            assert lib.scs_b200_accum_by_atrans(w, capi.dptr(yv), capi.dptr(aty), 0) == 0
+            assert lib.scs_solve_lin_sys(w, capi.dptr(sol), None, 1e-12) == 0
+            outs.append((ax, aty, sol))
+        finally:
+            lib.scs_free_lin_sys_work(w)
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+
+
 def test_spmv_full_size_c2_properties(lib):
     """BASELINE configs[1] size (n=1e6, m=3e6, nnz=1e7): parity of both operators against numpy in fp64,
     linearity, the adjoint identity <A x, y> = <x, A'y>, and run-to-run bit reproducibility."""

@@ -220,22 +220,40 @@ static void *dup_mem(const void *src, size_t bytes) {
 }
 
 /* ----------------------------------------------------------------- workspace */
+/* SCS_B200_SETUP_TIMING=1: wall-clock breakdown of scs_init / scs_finish on stderr (syncs the stream at every mark) */
+static void init_mark(const char *what, double *t_last) {
+  if (!getenv("SCS_B200_SETUP_TIMING")) return;
+  b200_sync();
+  {
+    const double t = now_ms();
+    fprintf(stderr, "scs_b200 setup: %-44s %8.1f ms\n", what, t - *t_last);
+    *t_last = t;
+  }
+}
+
 void scs_finish(ScsWork *w) {
+  double t_mark = now_ms();
   if (!w) return;
   b200_sync();
+  init_mark("finish: stream drained", &t_mark);
   if (w->log_csv_fout) fclose(w->log_csv_fout);
   free(w->log_csv_name);
   free(w->log_host);
   if (w->cones) b200_cones_destroy(w->cones);
+  init_mark("finish: cones", &t_mark);
   if (w->p) scs_free_lin_sys_work(w->p);
+  init_mark("finish: linear-system workspace", &t_mark);
   if (w->accel) b200_aa_destroy(w->accel);
+  init_mark("finish: acceleration workspace", &t_mark);
   b200_free(w->adm.d_u); b200_free(w->adm.d_u_t); b200_free(w->adm.d_v); b200_free(w->adm.d_v_prev);
   b200_free(w->adm.d_rsk); b200_free(w->adm.d_g); b200_free(w->adm.d_R); b200_free(w->adm.d_ws);
   b200_free(w->adm.d_sc); b200_free(w->adm.d_part); b200_free(w->adm.d_cnt);
   b200_free(w->d_b); b200_free(w->d_c); b200_free(w->d_D); b200_free(w->d_E);
   b200_free(w->d_ax); b200_free(w->d_aty); b200_free(w->d_px);
   b200_free(w->d_sol_x); b200_free(w->d_sol_y); b200_free(w->d_sol_s);
+  init_mark("finish: device vectors", &t_mark);
   b200_host_free(w->h_sc);
+  init_mark("finish: pinned scalars", &t_mark);
   free(w->D); free(w->E); free(w->b_orig); free(w->c_orig); free(w->h_diag_r);
   free(w->cone_boundaries);
   if (w->d) {
@@ -244,6 +262,7 @@ void scs_finish(ScsWork *w) {
   if (w->k) { free(w->k->bu); free(w->k->bl); free(w->k->q); free(w->k->s); free(w->k->p); free(w->k->cs); free(w->k); }
   free(w->stgs);
   free(w);
+  init_mark("finish: host copies", &t_mark);
 }
 
 static void set_diag_r_host(ScsWork *w) {
@@ -326,16 +345,6 @@ static void print_header(const ScsWork *w) {
            w->stgs->acceleration_lookback, w->stgs->acceleration_interval);
   printf("lin-sys:  %s\n\t  nnz(A): %li, nnz(P): %li\n", scs_get_lin_sys_method(),
          (long)w->nnzA, (long)w->nnzP);
-}
-
-static void init_mark(const char *what, double *t_last) {
-  if (!getenv("SCS_B200_SETUP_TIMING")) return;
-  b200_sync();
-  {
-    const double t = now_ms();
-    fprintf(stderr, "scs_b200 setup: %-44s %8.1f ms\n", what, t - *t_last);
-    *t_last = t;
-  }
 }
 
 ScsWork *scs_init(const ScsData *d, const ScsCone *k, const ScsSettings *stgs) {

@@ -89,6 +89,11 @@ static std::mutex g_pool_mu;
 static std::multimap<size_t, void *> g_pool_free;  // size -> block
 static std::map<void *, size_t> g_pool_size;       // every live or cached block we handed out -> its size
 static size_t g_pool_cached = 0;
+// pinned host blocks, cached the same way (see b200_host_alloc)
+static std::multimap<size_t, void *> g_hpool_free;
+static std::map<void *, size_t> g_hpool_size;
+static size_t g_hpool_cached = 0;
+#define B200_HPOOL_MAX_BYTES ((size_t)64 << 20)
 static int g_pool_on = -1;
 #define B200_POOL_MAX_BYTES ((size_t)24 << 30)
 static bool pool_enabled() {
@@ -105,6 +110,12 @@ static void pool_trim_locked() {
   }
   g_pool_free.clear();
   g_pool_cached = 0;
+  for (auto &kv : g_hpool_free) {
+    cudaFreeHost(kv.second);
+    g_hpool_size.erase(kv.second);
+  }
+  g_hpool_free.clear();
+  g_hpool_cached = 0;
 }
 extern "C" void scs_b200_release_memory(void) {
   if (g_init != 1) return;
@@ -162,15 +173,37 @@ extern "C" void b200_free(void *p) {
   g_pool_size.erase(it);
   cudaFree(p);
 }
+// pinned host blocks (a few control words and the AA's small R factor per workspace) are cached the same way:
+// cudaMallocHost / cudaFreeHost are device-wide synchronisations and cost far more than the blocks are worth
 extern "C" void *b200_host_alloc(size_t bytes) {
   if (b200_runtime_init() != 0) return nullptr;
   void *p = nullptr;
   if (bytes == 0) bytes = 16;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (pool_enabled()) {
+    auto it = g_hpool_free.find(bytes);
+    if (it != g_hpool_free.end()) {
+      p = it->second;
+      g_hpool_free.erase(it);
+      g_hpool_cached -= bytes;
+      return p;
+    }
+  }
   if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  g_hpool_size[p] = bytes;
   return p;
 }
 extern "C" void b200_host_free(void *p) {
-  if (p) cudaFreeHost(p);
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  auto it = g_hpool_size.find(p);
+  if (it != g_hpool_size.end() && pool_enabled() && g_hpool_cached + it->second <= B200_HPOOL_MAX_BYTES) {
+    g_hpool_free.insert({it->second, p});
+    g_hpool_cached += it->second;
+    return;
+  }
+  if (it != g_hpool_size.end()) g_hpool_size.erase(it);
+  cudaFreeHost(p);
 }
 
 // Host<->device copies. The caller's buffer may be pageable: stage through the

@@ -265,6 +265,30 @@ static void setup_mark(const char *what, double *t_last) {
   }
 }
 
+/* Both resident orientations of a CSC matrix: on the device when the builder takes it (kernels/setup.cu -- upload once,
+ * stable radix-sort transpose, flagged streams filled in HBM; bit-identical to the host builders), else by the host
+ * builders. *A_out = the m x n operator (rows of A), *At_out = the n x m one (rows of A' = columns of A). */
+static int build_both_ops(int m, int n, const int *Ap, const int *Ai, const double *Ax, B200Spmv **A_out,
+                          B200Spmv **At_out, double *t_mark) {
+  int *Tp = NULL, *Ti = NULL;
+  double *Tx = NULL;
+  const int rc_dev = b200_setup_ops_from_csc(m, n, Ap, Ai, Ax, A_out, At_out);
+  if (rc_dev < 0) return -1;
+  if (rc_dev == 0) {
+    setup_mark("linsys: both operators built on the device", t_mark);
+    return 0;
+  }
+  /* host builders: the CSR of A' is the CSC of A as given */
+  *At_out = b200_spmv_create(n, m, Ap, Ai, Ax);
+  setup_mark("linsys: operator A' (host plan + upload)", t_mark);
+  if (!*At_out || transpose_csc(m, n, Ap, Ai, Ax, &Tp, &Ti, &Tx) != 0) return -1;
+  setup_mark("linsys: host transpose", t_mark);
+  *A_out = b200_spmv_create(m, n, Tp, Ti, Tx);
+  setup_mark("linsys: operator A (host plan + upload)", t_mark);
+  free(Tp); free(Ti); free(Tx);
+  return *A_out ? 0 : -1;
+}
+
 /* The reordered pair used inside the CG operator (kernels/spmv.cu "Reordered copies"): built once, values and R_y
  * refreshed whenever the resident operators may have been rescaled (b200_linsys_update_diag_r_dev). */
 static int cg_ops_build(ScsLinSysWork *w) {
@@ -294,8 +318,6 @@ ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
                                      const scs_float *diag_r) {
   ScsLinSysWork *w;
   double t_mark = wall_ms();
-  int *Tp = NULL, *Ti = NULL;
-  double *Tx = NULL;
   int *Lp = NULL, *Li = NULL;
   double *Lx = NULL;
   const int n = A->n, m = A->m;
@@ -319,27 +341,15 @@ ScsLinSysWork *scs_init_lin_sys_work(const ScsMatrix *A, const ScsMatrix *P,
     w->row0 = w->offsets[w->rank];
     w->mloc = w->offsets[w->rank + 1] - w->row0;
     if (restrict_rows(n, A->p, A->i, A->x, w->row0, w->row0 + w->mloc, &Lp, &Li, &Lx) != 0) goto fail;
-    w->At = b200_spmv_create(n, w->mloc, Lp, Li, Lx);
-    if (transpose_csc(w->mloc, n, Lp, Li, Lx, &Tp, &Ti, &Tx) != 0) { free(Lp); free(Li); free(Lx); goto fail; }
-    w->A = b200_spmv_create(w->mloc, n, Tp, Ti, Tx);
-    free(Lp); free(Li); free(Lx);
-  } else {
-    /* device path first: upload the CSC once, transpose by a stable radix sort, build both flagged streams there */
-    const int rc_dev = b200_setup_ops_from_csc(m, n, A->p, A->i, A->x, &w->A, &w->At);
-    if (rc_dev < 0) goto fail;
-    if (rc_dev == 0) {
-      setup_mark("linsys: both operators built on the device", &t_mark);
-    } else {
-      /* host builders: CSR of A' is the CSC of A as given */
-      w->At = b200_spmv_create(n, m, A->p, A->i, A->x);
-      setup_mark("linsys: operator A' (host plan + upload)", &t_mark);
-      if (transpose_csc(m, n, A->p, A->i, A->x, &Tp, &Ti, &Tx) != 0) goto fail;
-      setup_mark("linsys: host transpose", &t_mark);
-      w->A = b200_spmv_create(m, n, Tp, Ti, Tx);
-      setup_mark("linsys: operator A (host plan + upload)", &t_mark);
+    setup_mark("linsys: row block cut out of A (host)", &t_mark);
+    {
+      const int rc = build_both_ops(w->mloc, n, Lp, Li, Lx, &w->A, &w->At, &t_mark);
+      free(Lp); free(Li); free(Lx);
+      if (rc != 0) goto fail;
     }
+  } else if (build_both_ops(m, n, A->p, A->i, A->x, &w->A, &w->At, &t_mark) != 0) {
+    goto fail;
   }
-  free(Tp); free(Ti); free(Tx);
   if (!w->A || !w->At) goto fail;
   if (P) {
     int *Fp = NULL, *Fi = NULL;
@@ -464,15 +474,12 @@ void scs_free_lin_sys_work(ScsLinSysWork *w) {
 /* Row-sharded setup: D, E of the FULL matrix are computed on every rank from temporary full
  * copies (both orientations) on its GPU; the resident local blocks are then scaled once. */
 int b200_linsys_full_equilibrate(const ScsMatrix *A, const int *bnd, int nbnd, double *d_D, double *d_E) {
-  int *Tp = NULL, *Ti = NULL, rc = -1;
-  double *Tx = NULL;
-  B200Spmv *At = b200_spmv_create(A->n, A->m, A->p, A->i, A->x);
-  B200Spmv *Ar = NULL;
-  if (At && transpose_csc(A->m, A->n, A->p, A->i, A->x, &Tp, &Ti, &Tx) == 0) {
-    Ar = b200_spmv_create(A->m, A->n, Tp, Ti, Tx);
-    if (Ar) rc = b200_equilibrate_dev(Ar, At, bnd, nbnd, d_D, d_E);
-  }
-  free(Tp); free(Ti); free(Tx);
+  int rc = -1;
+  double t_mark = wall_ms();
+  B200Spmv *At = NULL, *Ar = NULL;
+  if (build_both_ops(A->m, A->n, A->p, A->i, A->x, &Ar, &At, &t_mark) == 0)
+    rc = b200_equilibrate_dev(Ar, At, bnd, nbnd, d_D, d_E);
+  setup_mark("linsys: D, E from a temporary full copy", &t_mark);
   b200_spmv_destroy(Ar);
   b200_spmv_destroy(At);
   return rc;

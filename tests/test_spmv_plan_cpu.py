@@ -347,3 +347,52 @@ def test_long_rows_as_virtual_rows(lib, monkeypatch):
         y = np.array([yv[vptr[r]:vptr[r + 1]].sum() for r in range(nrows)])
         ref = np.array([np.dot(va[rp[r]:rp[r + 1]], x[ci[rp[r]:rp[r + 1]]]) for r in range(nrows)])
         assert np.abs(y - ref).max() <= 1e-12 * (np.abs(ref).max() + 1.0), trial
+
+
+def device_fill_restated(rp, ci, va):
+    """numpy restatement of k_fill_flagged (kernels/spmv.cu, the device builder's fill kernel): one stored entry per
+    nonzero, one SKIP|END zero per empty row, an END at the end of every balanced piece of a long row."""
+    idx, vals = [], []
+    for r in range(len(rp) - 1):
+        a, b = int(rp[r]), int(rp[r + 1])
+        ln = b - a
+        if ln == 0:
+            idx.append(END | SKIP)
+            vals.append(0.0)
+            continue
+        if ln <= MAXROW:
+            ends = {ln - 1}
+        else:
+            pieces = -(-ln // MAXROW)
+            small, big = divmod(ln, pieces)
+            left, q, ends = small + (1 if big > 0 else 0), 0, set()
+            for j in range(ln):
+                left -= 1
+                if left == 0:
+                    ends.add(j)
+                    q += 1
+                    left = small + (1 if q < big else 0)
+        for j in range(ln):
+            idx.append(int(ci[a + j]) | (END if j in ends else 0))
+            vals.append(va[a + j])
+    return np.array(idx, dtype=np.uint32), np.array(vals)
+
+
+def test_device_fill_rule_equals_host_plan_stream(lib, monkeypatch):
+    """The device builder (b200_spmv_create_dev) cuts long rows with its own kernel; the rule restated above must give
+    exactly the stream of the host plan builder (the hardware test of the real kernel:
+    tests/test_linsys_gpu.py::test_device_built_operators_equal_host_built)."""
+    monkeypatch.delenv("SCS_B200_SPMV_LONGROWS", raising=False)
+    rng = np.random.default_rng(77)
+    for nrows, ncols, sampler in [
+        (40, 3000, lambda: rng.choice([0, 1, 3, 124, 125, 200, 248, 249, 373, 700, 1500], 40)),
+        (500, 900, lambda: np.where(rng.random(500) < 0.1, rng.integers(125, 900, 500), rng.poisson(4, 500))),
+        (3, 2000, lambda: np.array([2000, 0, 1999])),
+        (200, 50, lambda: rng.poisson(3, 200)),
+    ]:
+        lens = np.minimum(sampler(), ncols)
+        rp, ci, va = random_csr(nrows, ncols, rng, lens)
+        plan = build_plan(lib, nrows, ncols, rp, ci, va, 7)
+        idx, vals = device_fill_restated(rp, ci, va)
+        assert np.array_equal(idx, plan["idx"])
+        assert np.array_equal(vals, plan["vals"])

@@ -333,12 +333,17 @@ def test_sigint_stops_a_long_solve(lib):
     import threading
     prob = small_problem("socp", seed=9)
     before = signal.getsignal(signal.SIGINT)
-    t = threading.Timer(0.5, lambda: os.kill(os.getpid(), signal.SIGINT))
-    t.start()
+    # two shots: should the first SIGINT land before scs_solve has installed its listener (a slow scs_init on a loaded
+    # box) the second one still stops the solve; max_iters is finite so that a missed signal FAILS the test after a
+    # minute or two instead of hanging the suite
+    timers = [threading.Timer(d, lambda: os.kill(os.getpid(), signal.SIGINT)) for d in (0.5, 3.0)]
+    for t in timers:
+        t.start()
     try:
-        st, info, x, y, s = solve_with(lib, prob, eps_abs=0.0, eps_rel=0.0, eps_infeas=0.0, max_iters=100000000)
+        st, info, x, y, s = solve_with(lib, prob, eps_abs=0.0, eps_rel=0.0, eps_infeas=0.0, max_iters=300000)
     finally:
-        t.cancel()
+        for t in timers:
+            t.cancel()
     assert st == -5, (st, info.status)
     assert info.status.decode() == "interrupted" and info.iter == -1 and np.isnan(x).all()
     assert signal.getsignal(signal.SIGINT) == before

@@ -331,22 +331,36 @@ def test_sigint_stops_a_long_solve(lib):
     import os
     import signal
     import threading
+    import time
     prob = small_problem("socp", seed=9)
-    before = signal.getsignal(signal.SIGINT)
-    # two shots: should the first SIGINT land before scs_solve has installed its listener (a slow scs_init on a loaded
-    # box) the second one still stops the solve; max_iters is finite so that a missed signal FAILS the test after a
-    # minute or two instead of hanging the suite
-    timers = [threading.Timer(d, lambda: os.kill(os.getpid(), signal.SIGINT)) for d in (0.5, 3.0)]
-    for t in timers:
-        t.start()
+    hits = []
+    # a recording Python-level handler for the duration of the test: a SIGINT that lands outside the library's
+    # listener window must not raise KeyboardInterrupt (pytest would abort the whole session)
+    before = signal.signal(signal.SIGINT, lambda *a: hits.append(1))
     try:
-        st, info, x, y, s = solve_with(lib, prob, eps_abs=0.0, eps_rel=0.0, eps_infeas=0.0, max_iters=300000)
-    finally:
+        # two shots: should the first SIGINT land before scs_solve has installed its listener (a slow scs_init on a
+        # loaded box) the second one still stops the solve; max_iters is finite so that a missed signal FAILS the
+        # test after a minute or two instead of hanging the suite
+        timers = [threading.Timer(d, lambda: os.kill(os.getpid(), signal.SIGINT)) for d in (0.5, 3.0)]
         for t in timers:
-            t.cancel()
-    assert st == -5, (st, info.status)
-    assert info.status.decode() == "interrupted" and info.iter == -1 and np.isnan(x).all()
-    assert signal.getsignal(signal.SIGINT) == before
+            t.start()
+        try:
+            st, info, x, y, s = solve_with(lib, prob, eps_abs=0.0, eps_rel=0.0, eps_infeas=0.0, max_iters=300000)
+        finally:
+            for t in timers:
+                t.cancel()
+        assert st == -5, (st, info.status)
+        assert info.status.decode() == "interrupted" and info.iter == -1 and np.isnan(x).all()
+        # the previous handler is back in place: a SIGINT sent now reaches the Python-level handler again
+        n0 = len(hits)
+        os.kill(os.getpid(), signal.SIGINT)
+        for _ in range(100):
+            if len(hits) > n0:
+                break
+            time.sleep(0.01)
+        assert len(hits) == n0 + 1
+    finally:
+        signal.signal(signal.SIGINT, before)
     # and the library still works
     st, info, *_ = solve_with(lib, prob)
     assert st == 1

@@ -244,8 +244,9 @@ scs_int scs_b200_comm_init(scs_int rank, scs_int nranks, const char *id128);
 scs_int scs_b200_comm_finalize(void);
 /* peer-memory reduction of the sharded CG: 0 automatic, 1 one pass, 2 reduce-scatter + all-gather */
 void scs_b200_set_p2p_mode(int mode);
-/* STAGED, off by default, not yet run on hardware: "sharded-x" CG iteration (x, r, z, Gp owned by n-slices, one
- * cooperative kernel per rank and iteration; kernels/cg.cu k_cgx_iteration). Also SCS_B200_SHARD_X=1. */
+/* "sharded-x" push mode of the multi-GPU CG (x, r, z, Gp owned by n-slices, one slice kernel per rank and iteration;
+ * kernels/cg.cu k_cgx_iteration): the DEFAULT since round 2; 0 selects the replicated modes above.
+ * Also SCS_B200_SHARD_X=0/1. */
 void scs_b200_set_shard_x(int on);
 /* contiguous row blocks of A balanced by nonzeros: offsets[nranks+1] (host logic, no GPU needed) */
 scs_int scs_b200_row_partition(scs_int m, scs_int n, const scs_int *Ap, const scs_int *Ai,

@@ -198,9 +198,34 @@ static int expand_sym_upper(int n, const int *Pp, const int *Pi, const double *P
 
 /* Row partition for the sharded KKT solve: contiguous blocks with (nearly) equal
  * numbers of nonzeros. */
+/* generic fork-join over an array of job records (same policy as tr_run: threads that cannot be created run inline) */
+static void run_jobs(void *(*fn)(void *), void *jobs, size_t stride, int T) {
+  pthread_t th[64];
+  int t, started = 0;
+  for (t = 1; t < T; ++t) {
+    if (pthread_create(&th[t], NULL, fn, (char *)jobs + (size_t)t * stride) != 0) break;
+    started = t;
+  }
+  fn(jobs);
+  for (t = started + 1; t < T; ++t) fn((char *)jobs + (size_t)t * stride);
+  for (t = 1; t <= started; ++t) pthread_join(th[t], NULL);
+}
+
+typedef struct {
+  long long k0, k1;
+  const int *Ai;
+  int *cnt;
+} PcJob;
+static void *pc_worker(void *arg) { /* entries per row: integer counts, order-independent */
+  PcJob *jb = (PcJob *)arg;
+  long long k;
+  for (k = jb->k0; k < jb->k1; ++k) __atomic_fetch_add(&jb->cnt[jb->Ai[k]], 1, __ATOMIC_RELAXED);
+  return NULL;
+}
+
 void b200_row_partition(int m, int n, const int *Ap, const int *Ai, int nranks, int *offsets) {
   const long long nnz = Ap[n];
-  long long *cnt = (long long *)calloc((size_t)m + 1, sizeof(long long));
+  int *cnt = (int *)calloc((size_t)m + 1, sizeof(int));
   long long acc = 0;
   int i, r = 1;
   offsets[0] = 0;
@@ -208,9 +233,17 @@ void b200_row_partition(int m, int n, const int *Ap, const int *Ai, int nranks, 
     for (r = 1; r <= nranks; ++r) offsets[r] = (int)(((long long)m * r) / nranks);
     return;
   }
-  for (i = 0; i < nnz; ++i) cnt[Ai[i]]++;
+  {
+    PcJob jobs[64];
+    const int T = b200_host_threads(nnz);
+    int t;
+    for (t = 0; t < T; ++t) {
+      jobs[t].k0 = nnz * t / T; jobs[t].k1 = nnz * (t + 1) / T; jobs[t].Ai = Ai; jobs[t].cnt = cnt;
+    }
+    run_jobs(pc_worker, jobs, sizeof(PcJob), T);
+  }
   for (i = 0; i < m && r < nranks; ++i) {
-    acc += cnt[i] + 1; /* +1: empty rows still cost a row */
+    acc += (long long)cnt[i] + 1; /* +1: empty rows still cost a row */
     while (r < nranks && acc >= ((nnz + m) * (long long)r) / nranks) offsets[r++] = i + 1;
   }
   while (r <= nranks) offsets[r++] = m;
@@ -224,28 +257,78 @@ scs_int scs_b200_row_partition(scs_int m, scs_int n, const scs_int *Ap, const sc
   return 0;
 }
 
-/* CSC restricted to rows [r0, r1), row indices shifted by -r0 */
+/* CSC restricted to rows [r0, r1), row indices shifted by -r0. Threaded over column ranges of equal nnz: a count pass
+ * (kept entries per column), a serial prefix over the n columns, a fill pass -- the output does not depend on the
+ * number of threads. */
+typedef struct {
+  int j0, j1, r0, r1, phase;
+  const int *Ap, *Ai;
+  const double *Ax;
+  int *Lp, *Li;
+  double *Lx;
+} RrJob;
+static void *rr_worker(void *arg) {
+  RrJob *jb = (RrJob *)arg;
+  const int r0 = jb->r0, r1 = jb->r1;
+  int j, k;
+  if (jb->phase == 0) {
+    for (j = jb->j0; j < jb->j1; ++j) {
+      int c = 0;
+      for (k = jb->Ap[j]; k < jb->Ap[j + 1]; ++k) c += (jb->Ai[k] >= r0 && jb->Ai[k] < r1);
+      jb->Lp[j + 1] = c;
+    }
+  } else {
+    for (j = jb->j0; j < jb->j1; ++j) {
+      int q = jb->Lp[j];
+      for (k = jb->Ap[j]; k < jb->Ap[j + 1]; ++k)
+        if (jb->Ai[k] >= r0 && jb->Ai[k] < r1) { jb->Li[q] = jb->Ai[k] - r0; jb->Lx[q] = jb->Ax[k]; ++q; }
+    }
+  }
+  return NULL;
+}
 static int restrict_rows(int n, const int *Ap, const int *Ai, const double *Ax, int r0, int r1,
                          int **Lp_out, int **Li_out, double **Lx_out) {
-  int j, k, cnt = 0;
+  RrJob jobs[64];
+  const long long nnz = Ap[n];
+  int T = b200_host_threads(nnz);
+  int j, t, cnt;
   int *Lp = (int *)calloc((size_t)n + 1, sizeof(int));
   int *Li;
   double *Lx;
   if (!Lp) return -1;
-  for (j = 0; j < n; ++j) {
-    for (k = Ap[j]; k < Ap[j + 1]; ++k)
-      if (Ai[k] >= r0 && Ai[k] < r1) cnt++;
-    Lp[j + 1] = cnt;
+  if (T > n) T = n > 0 ? n : 1;
+  for (t = 0, j = 0; t < T; ++t) { /* column ranges balanced by their number of entries */
+    const long long target = nnz * (t + 1) / T;
+    jobs[t].j0 = j;
+    if (t == T - 1) {
+      j = n;
+    } else {
+      int lo = j, hi = n;
+      while (lo < hi) {
+        const int mid = lo + (hi - lo) / 2;
+        if (Ap[mid] < target) lo = mid + 1; else hi = mid;
+      }
+      j = lo;
+    }
+    jobs[t].j1 = j;
+    jobs[t].r0 = r0; jobs[t].r1 = r1; jobs[t].phase = 0;
+    jobs[t].Ap = Ap; jobs[t].Ai = Ai; jobs[t].Ax = Ax; jobs[t].Lp = Lp; jobs[t].Li = NULL; jobs[t].Lx = NULL;
   }
+  run_jobs(rr_worker, jobs, sizeof(RrJob), T);
+  for (j = 0; j < n; ++j) Lp[j + 1] += Lp[j];
+  cnt = Lp[n];
   Li = (int *)malloc(((size_t)cnt + 1) * sizeof(int));
   Lx = (double *)malloc(((size_t)cnt + 1) * sizeof(double));
   if (!Li || !Lx) { free(Lp); free(Li); free(Lx); return -1; }
-  cnt = 0;
-  for (j = 0; j < n; ++j)
-    for (k = Ap[j]; k < Ap[j + 1]; ++k)
-      if (Ai[k] >= r0 && Ai[k] < r1) { Li[cnt] = Ai[k] - r0; Lx[cnt] = Ax[k]; cnt++; }
+  for (t = 0; t < T; ++t) { jobs[t].phase = 1; jobs[t].Li = Li; jobs[t].Lx = Lx; }
+  run_jobs(rr_worker, jobs, sizeof(RrJob), T);
   *Lp_out = Lp; *Li_out = Li; *Lx_out = Lx;
   return 0;
+}
+/* test entry point (tests/test_sharding_cpu.py); the arrays are malloc'ed, the caller frees them */
+int scs_b200_restrict_rows_csc(int n, const int *Ap, const int *Ai, const double *Ax, int r0, int r1, int **Lp_out,
+                               int **Li_out, double **Lx_out) {
+  return restrict_rows(n, Ap, Ai, Ax, r0, r1, Lp_out, Li_out, Lx_out);
 }
 
 #include <time.h>

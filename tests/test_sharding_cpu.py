@@ -103,3 +103,47 @@ def test_row_partition_edge_cases():
         assert lib.scs_b200_row_partition(m, n, capi.iptr(ptr), capi.iptr(idx), world, capi.iptr(offs)) == 0
         assert offs[0] == 0 and offs[-1] == m
         assert np.all(np.diff(offs) >= 0)
+
+
+@pytest.mark.parametrize("threads", ["1", "3", "16"])
+def test_row_block_extraction_is_thread_count_independent(threads, monkeypatch):
+    """every rank cuts its row block out of the user's CSC on the host (threaded over column ranges of equal nnz,
+    host/linsys_b200.c restrict_rows) before the device builder takes over: same arrays as numpy for any thread count,
+    and the per-row counts behind scs_b200_row_partition (threaded, atomic integer counts) give the same offsets."""
+    sys.path.insert(0, ROOT)
+    from scs_b200 import capi, problems
+    lib = capi.load()
+    ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+    lib.scs_b200_restrict_rows_csc.restype = C.c_int
+    lib.scs_b200_restrict_rows_csc.argtypes = [C.c_int, ip, ip, dp, C.c_int, C.c_int, C.POINTER(ip), C.POINTER(ip), C.POINTER(dp)]
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    rng = np.random.default_rng(5)
+    for m, n, per in ((50, 20, 3), (90000, 60000, 10), (300, 70000, 8)):
+        data, idx, ptr, _ = problems.random_sparse_csc(m, n, per, rng)
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        ptr = np.ascontiguousarray(ptr, dtype=np.int32)
+        data = np.ascontiguousarray(data)
+        monkeypatch.setenv("SCS_B200_HOST_THREADS", "1")
+        base = np.zeros(4, dtype=np.int32)
+        assert lib.scs_b200_row_partition(m, n, capi.iptr(ptr), capi.iptr(idx), 3, capi.iptr(base)) == 0
+        monkeypatch.setenv("SCS_B200_HOST_THREADS", threads)
+        offs = np.zeros(4, dtype=np.int32)
+        assert lib.scs_b200_row_partition(m, n, capi.iptr(ptr), capi.iptr(idx), 3, capi.iptr(offs)) == 0
+        assert np.array_equal(offs, base)
+        cols = np.repeat(np.arange(n), np.diff(ptr))
+        for g in range(3):
+            r0, r1 = int(offs[g]), int(offs[g + 1])
+            lp, li, lx = ip(), ip(), dp()
+            assert lib.scs_b200_restrict_rows_csc(n, ptr.ctypes.data_as(ip), idx.ctypes.data_as(ip), data.ctypes.data_as(dp),
+                                                  r0, r1, C.byref(lp), C.byref(li), C.byref(lx)) == 0
+            keep = (idx >= r0) & (idx < r1)
+            want_p = np.concatenate([[0], np.cumsum(np.bincount(cols[keep], minlength=n))])
+            got_p = np.ctypeslib.as_array(lp, (n + 1,)).copy()
+            cnt = int(got_p[-1])
+            got_i = np.ctypeslib.as_array(li, (max(cnt, 1),))[:cnt].copy()
+            got_x = np.ctypeslib.as_array(lx, (max(cnt, 1),))[:cnt].copy()
+            for q in (lp, li, lx):
+                libc.free(C.cast(q, C.c_void_p))
+            assert np.array_equal(got_p, want_p)
+            assert np.array_equal(got_i, idx[keep] - r0) and np.array_equal(got_x, data[keep])

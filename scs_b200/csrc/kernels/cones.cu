@@ -77,7 +77,7 @@ struct B200Cones {
   int n_ep, n_ed, n_pow;
   long long tri_off;  // first row of the exponential triples
   double *d_pow;      // power cone parameters (sign = primal / dual), psize
-  B200CpsdCones *cpsd;  // complex PSD blocks (kernels/cones_complex.cu; staged, see there), or NULL
+  B200CpsdCones *cpsd;  // complex PSD blocks (kernels/cones_complex.cu), or NULL
   // sticky device flag: OR of every per-matrix `info` the batched eigen-solver has returned (reference
   // cones.c:1048-1052 propagates a failed syevr as "error in project_cones"); read by b200_cones_check
   int *d_err;

@@ -1,4 +1,4 @@
-"""CPU: the index arithmetic of the staged complex-PSD kernels (scs_b200/csrc/kernels/cones_complex.cu:
+"""CPU: the index arithmetic of the complex-PSD kernels (scs_b200/csrc/kernels/cones_complex.cu:
 k_cpsd_unpack / k_cpsd_reconstruct -- packed Hermitian block <-> real embedding [[A, -B], [B, A]] of order 2k),
 restated in numpy line by line and checked against the reference's zheevr-based projection
 (oracle/_ref: src/cones.c:1072-1156 through _scs_proj_dual_cone)."""
